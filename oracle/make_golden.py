@@ -1,0 +1,206 @@
+"""Generate tests/golden/* from the REFERENCE ITSELF (run in the build container only).
+
+    python -m oracle.make_golden          # from the repo root; needs /root/reference
+
+Sources of truth used here:
+  * the reference's shipped native binaries, executed through oracle/refbin.py (rANS, pmf->cdf);
+  * the reference's unmodified Python modules, imported through oracle/refshim.py
+    (entropy_models.py, models/stf.py), on the CPU in fp32.
+Nothing under oracle/*.c / oracle/entropy.py / oracle/stf_ref.py (the restatements) is used to
+PRODUCE a fixture; tests/test_oracle_pinned.py replays the fixtures against those restatements.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+GOLD = os.path.join(REPO, "tests", "golden")
+
+from oracle import refbin, refshim, weights  # noqa: E402
+
+
+def sha1(b):
+    return hashlib.sha1(b).hexdigest()
+
+
+def seeded_stream(n, seed, table, kind="uniform"):
+    """SURVEY.md §8c/§8d synthetic (symbols, indexes)."""
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        idx = rng.integers(0, 64, n)
+    elif kind == "lowrate":
+        idx = np.minimum(rng.geometric(0.15, n) - 1, 63)
+    elif kind == "zero":
+        idx = np.zeros(n, np.int64)
+    sym = np.rint(rng.normal(0, table[idx])).astype(np.int32)
+    if kind == "zero":
+        sym[:] = 0
+    return sym, idx.astype(np.int32)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    h = refshim.install("binary")
+    stf, em = h["stf"], h["entropy_models"]
+    torch.manual_seed(0)
+
+    # ---------------------------------------------------------------- tables (reference update())
+    gc = em.GaussianConditional(None)
+    gc.update_scale_table(stf.get_scale_table())
+    cdf = gc._quantized_cdf.numpy().astype(np.int32)
+    lengths = gc._cdf_length.numpy().astype(np.int32)
+    offsets = gc._offset.numpy().astype(np.int32)
+    table = gc.scale_table.numpy()
+    assert sha1(cdf.astype("<i4").tobytes()) == "5000194aa652d73520578889b0d0b77c61a7d389"
+
+    kat = {"pmf": [], "rans_small": [], "streams": [], "gc_table_sha1": sha1(cdf.astype("<i4").tobytes())}
+    # ---------------------------------------------------------------- R5 KATs
+    rng = np.random.default_rng(7)
+    pmfs = [[0.25, 0.5, 0.25], [0.1, 0.2, 0.3, 0.4], [1e-9, 0.999999, 1e-9, 1e-9], [0.5, 0, 0, 0.5], [1 / 3, 1 / 3, 1 / 3]]
+    for n in (2, 7, 33, 257):
+        p = rng.random(n) ** 4
+        p[rng.integers(0, n, max(1, n // 5))] = 0.0
+        pmfs.append((p / p.sum()).astype(np.float32).tolist())
+    for p in pmfs:
+        for prec in (16, 12):
+            if len(p) + 1 > (1 << prec):
+                continue
+            kat["pmf"].append({"pmf": [float(np.float32(v)) for v in p], "precision": prec,
+                               "cdf": refbin.pmf_to_quantized_cdf(p, prec).tolist()})
+    # ---------------------------------------------------------------- R1-R4 small KATs
+    small_cdfs = np.array([[0, 16384, 49152, 65536, 0, 0], [0, 1, 32768, 65535, 65536, 0]], np.int32)
+    small = [([-1, 0, -1, 0], [0, 0, 0, 0]), ([0, 1, -1, 0, 1, -1, 0, 0], [1, 1, 1, 0, 1, 0, 1, 0]),
+             ([1, 0, 0, 0], [0, 0, 0, 0]), ([-2, 0, 0, 0], [0, 0, 0, 0]), ([100000, 0, 0, 0], [0, 0, 0, 0]),
+             ([-100000, 0, 0, 0], [1, 0, 0, 0]), ([0, 0, 0], [0, 1, 0]), ([7, -9, 33, -1000, 12345678, 0, 2], [1, 0, 1, 0, 1, 0, 1]),
+             ([15, -15, 16, -16, 255, -256, 4095, 4096, 65535, -65536, 1 << 20, -(1 << 20), (1 << 26), -(1 << 26)], [0] * 14)]
+    for s, i in small:
+        b = refbin.RansEncoder().encode_with_indexes(s, i, small_cdfs, [4, 5], [-1, -1])
+        d = refbin.RansDecoder().decode_with_indexes(b, i, small_cdfs, [4, 5], [-1, -1])
+        assert d.tolist() == list(s)
+        kat["rans_small"].append({"symbols": s, "indexes": i, "hex": b.hex()})
+    kat["small_tables"] = {"cdfs": small_cdfs.tolist(), "sizes": [4, 5], "offsets": [-1, -1]}
+    # ---------------------------------------------------------------- seeded streams on the real GC tables
+    for n, seed, kind in [(1000, 1, "uniform"), (49152, 2, "uniform"), (589824, 1234, "uniform"), (49152, 3, "lowrate"),
+                          (49152, 4, "zero"), (4096, 5, "uniform")]:
+        sym, idx = seeded_stream(n, seed, table, kind)
+        if seed == 5:  # adversarial: bypass boundaries and long escapes
+            c = -offsets[idx]
+            sym = np.where(np.arange(n) % 4 == 0, c, np.where(np.arange(n) % 4 == 1, -c, np.where(np.arange(n) % 4 == 2, c + 1, -c - 1))).astype(np.int32)
+            sym[::97] = 100000
+            sym[1::97] = -100000
+        b = refbin.RansEncoder().encode_with_indexes(sym, idx, cdf, lengths, offsets)
+        d = refbin.RansDecoder().decode_with_indexes(b, idx, cdf, lengths, offsets)
+        assert np.array_equal(d, sym)
+        # split decode (decode_stream x3) and buffered multi-call encode behave like one-shot
+        e = refbin.BufferedRansEncoder()
+        k = n // 3
+        e.encode_with_indexes(sym[:k], idx[:k], cdf, lengths, offsets)
+        e.encode_with_indexes(sym[k:], idx[k:], cdf, lengths, offsets)
+        assert e.flush() == b
+        kat["streams"].append({"n": n, "seed": seed, "kind": kind if seed != 5 else "adversarial",
+                               "nbytes": len(b), "sha1": sha1(b), "sym_sha1": sha1(sym.astype("<i4").tobytes())})
+    with open(os.path.join(GOLD, "rans_kat.json"), "w") as f:
+        json.dump(kat, f)
+
+    # pmf rows (floats) for three tables, so pmf->cdf can be replayed without torch's erfc
+    mult = -gc._standardized_quantile(gc.tail_mass / 2)
+    np.savez_compressed(
+        os.path.join(GOLD, "gc_tables.npz"), scale_table=table, cdf_length=lengths, offset=offsets,
+        row0=cdf[0, : lengths[0]], row10=cdf[10, : lengths[10]], row40=cdf[40, : lengths[40]], row63=cdf[63, : lengths[63]],
+        multiplier=np.float64(mult),
+    )
+
+    # ---------------------------------------------------------------- entropy-model KATs (reference python)
+    g = torch.Generator().manual_seed(11)
+    logu = torch.exp(torch.empty(20000).uniform_(np.log(0.01), np.log(400.0), generator=g))
+    t = torch.from_numpy(table)
+    edge = torch.cat([t, torch.nextafter(t, torch.tensor(0.0)), torch.nextafter(t, torch.tensor(1e9)),
+                      torch.tensor([0.0, -1.0, 0.11, 256.0, 1e9, 0.10999999])])
+    scales = torch.cat([logu, edge])
+    idx_ref = gc.build_indexes(scales).numpy().astype(np.int32)
+    means = torch.randn(scales.shape, generator=g) * 2
+    y = means + torch.randn(scales.shape, generator=g) * scales.clamp(0.05, 50)
+    y[:6] = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, -2.5]) + means[:6]
+    gc.eval()
+    with torch.no_grad():
+        y_hat, lik = gc(y, scales, means)
+        sym = gc.quantize(y, "symbols", means)
+    eb = em.EntropyBottleneck(192)
+    ebsd = weights.seeded_state_dict(eb.state_dict(), seed=3, stress=False)
+    eb.load_state_dict({k: v for k, v in ebsd.items() if k in dict(eb.named_parameters())}, strict=False)
+    eb.update(force=True)
+    eb.eval()
+    z = torch.randn(2, 192, 3, 5, generator=g) * 4
+    with torch.no_grad():
+        z_hat, z_lik = eb(z)
+        z_strings = eb.compress(z)
+        z_dec = eb.decompress(z_strings, z.shape[-2:])
+    assert torch.equal(z_dec, z_hat)
+    np.savez_compressed(
+        os.path.join(GOLD, "entropy_kat.npz"),
+        scales=scales.numpy(), indexes=idx_ref, means=means.numpy(), y=y.numpy(), y_hat=y_hat.numpy(),
+        y_lik=lik.numpy(), symbols=sym.numpy(),
+        eb_cdf=eb._quantized_cdf.numpy(), eb_len=eb._cdf_length.numpy(), eb_off=eb._offset.numpy(),
+        z=z.numpy(), z_hat=z_hat.numpy(), z_lik=z_lik.numpy(),
+        z_string0=np.frombuffer(z_strings[0], np.uint8), z_string1=np.frombuffer(z_strings[1], np.uint8),
+    )
+
+    # ---------------------------------------------------------------- model-level: STF 128x192, seeded stress weights
+    m = stf.SymmetricalTransFormer().eval()
+    sd = weights.seeded_state_dict(m.state_dict(), seed=0, stress=True)
+    m.load_state_dict(sd)
+    m.update(force=True)
+    x = weights.seeded_image((1, 3, 128, 192), seed=0)
+    rec = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            rec.setdefault(name, []).append(out.detach().clone())
+        return f
+
+    hs = []
+    for i in range(12):
+        hs.append(m.cc_mean_transforms[i].register_forward_hook(hook("mu")))
+        hs.append(m.cc_scale_transforms[i].register_forward_hook(hook("scale")))
+    hs.append(m.h_a.register_forward_hook(hook("z")))
+    hs.append(m.h_mean_s.register_forward_hook(hook("lm")))
+    hs.append(m.h_scale_s.register_forward_hook(hook("ls")))
+    hs.append(m.layers[3].register_forward_hook(lambda mod, i, o: rec.setdefault("y_tok", []).append(o[0].detach().clone())))
+    with torch.no_grad():
+        out = m(x)
+        fwd = {k: [t.clone() for t in v] for k, v in rec.items()}
+        rec.clear()
+        c = m.compress(x)
+        d = m.decompress(c["strings"], c["shape"])
+    for hh in hs:
+        hh.remove()
+    assert torch.equal(d["x_hat"], out["x_hat"].clamp(0, 1))
+    y_tok = fwd["y_tok"][0]
+    yv = y_tok.view(1, 8, 12, 384).permute(0, 3, 1, 2).contiguous()
+    mu = torch.cat(fwd["mu"], 1)
+    sc = torch.cat(fwd["scale"], 1)
+    sym = torch.round(yv - mu).int()
+    idx = m.gaussian_conditional.build_indexes(sc)
+    print("stf_small: y-string", len(c["strings"][0][0]), "B z-string", len(c["strings"][1][0]), "B; distinct idx", idx.unique().numel(),
+          "max|sym|", int(sym.abs().max()), "psnr", float(-10 * torch.log10(torch.mean((x - d['x_hat']) ** 2))))
+    np.savez_compressed(
+        os.path.join(GOLD, "stf_small.npz"),
+        y=yv.numpy(), z=fwd["z"][0].numpy(), latent_means=fwd["lm"][0].numpy(), latent_scales=fwd["ls"][0].numpy(),
+        mu=mu.numpy(), scale=sc.numpy(), symbols=sym.numpy().astype(np.int32), indexes=idx.numpy().astype(np.uint8),
+        x_hat=out["x_hat"].numpy(), y_lik=out["likelihoods"]["y"].numpy(), z_lik=out["likelihoods"]["z"].numpy(),
+        y_string=np.frombuffer(c["strings"][0][0], np.uint8), z_string=np.frombuffer(c["strings"][1][0], np.uint8),
+        eb_cdf=m.entropy_bottleneck._quantized_cdf.numpy(), eb_len=m.entropy_bottleneck._cdf_length.numpy(),
+        eb_off=m.entropy_bottleneck._offset.numpy(),
+    )
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()
