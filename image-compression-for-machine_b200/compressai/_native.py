@@ -1,0 +1,133 @@
+"""ctypes binding of libicm_b200.so (the C-ABI CUDA library, include/icm_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.  PyTorch is
+used only for device memory (tensor.data_ptr()) and the current CUDA stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "lib", "libicm_b200.so")
+
+ACT_NONE, ACT_GELU, ACT_HALF_TANH, ACT_SIGMOID = 0, 1, 2, 3
+OUT_BF16, OUT_F32 = 0, 1
+EB_PARAMS = 59
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sc", C.c_int64), ("sp", C.c_int64)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("inp", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("residual", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("in_pitch", C.c_int),
+        ("Cout", C.c_int), ("out_pitch", C.c_int), ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+        ("act", C.c_int), ("out_dtype", C.c_int), ("pixel_shuffle", C.c_int), ("res_pitch", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the library (building it first if nvcc is available and it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("_icm_build", os.path.join(_PKG, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as e:  # noqa: BLE001
+            raise NativeError(
+                f"{LIB_PATH} is missing and could not be built ({e}); run `python image-compression-for-machine_b200/build.py`. "
+                "There is no CPU fallback for this path."
+            ) from e
+    L = C.CDLL(LIB_PATH)
+    P, I, I64, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    sig = {
+        "icm_last_error": (C.c_char_p, []),
+        "icm_abi_version": (I, []),
+        "icm_launch_count": (I64, []),
+        "icm_pmf_to_quantized_cdf": (I, [P, I, I, P]),
+        "icm_tables_create": (I, [P, I, I, P, P, C.POINTER(P)]),
+        "icm_tables_destroy": (None, [P]),
+        "icm_rans_encode_workspace_bytes": (I64, [I, I64]),
+        "icm_rans_encode_batch": (I, [P, P, P, I, I64, P, P, I64, P, P]),
+        "icm_rans_decoder_create": (I, [I, C.POINTER(P)]),
+        "icm_rans_decoder_destroy": (None, [P]),
+        "icm_rans_decoder_set_streams": (I, [P, P, P, P, P]),
+        "icm_rans_decoder_step": (I, [P, P, P, I64, P, P]),
+        "icm_rans_decoder_status": (I, [P, P, P]),
+        "icm_gc_quantize_index": (I, [View, View, View, I, I, I64, P, I, F, P, P, I64, I64, View, View, View, P]),
+        "icm_gc_build_indexes": (I, [View, I, I, I64, P, I, F, P, I64, I64, P]),
+        "icm_gc_dequantize": (I, [P, I64, I64, View, I, I, I64, View, View, View, P]),
+        "icm_gc_likelihood": (I, [View, View, View, I, I, I64, F, F, View, View, View, View, P]),
+        "icm_add_lrp": (I, [View, View, I, I, I64, View, View, P]),
+        "icm_eb_process": (I, [I, View, I, I, I64, P, F, P, P, View, View, View, P]),
+        "icm_conv2d": (I, [C.POINTER(ConvArgs), P]),
+        "icm_pack_conv_weight": (I, [P, I, I, I, I, I, I, I, P, P]),
+        "icm_layernorm": (I, [P, P, P, P, I, I64, I, I, I, I, I, P]),
+        "icm_cast_bf16": (I, [P, I64, I, I64, P, I64, P]),
+        "icm_window_attention": (I, [P, P, P, I, I, I, I, I, I, I, P]),
+        "icm_patch_embed": (I, [P, P, P, P, P, P, I, I, I, I, P]),
+        "icm_final_conv": (I, [P, P, P, P, I, I, I, I, I, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    L._icm_symbols = tuple(sig)
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc is not None and rc < 0:
+        msg = lib().icm_last_error().decode(errors="replace")
+        raise NativeError(f"{what} failed ({rc}): {msg}")
+    return rc
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise NativeError(f"{name} must live on a CUDA device: this path has no CPU implementation")
+
+
+NULL_VIEW = View(None, 0, 0, 0)
+
+
+def view_bcp(t, B, Cc, P, channel_offset=0):
+    """View of a contiguous channels-last [B, P, pitch] tensor restricted to channels [off, off+C)."""
+    if t is None:
+        return NULL_VIEW
+    pitch = t.shape[-1]
+    return View(t.data_ptr() + channel_offset * t.element_size(), P * pitch, 1, pitch)
+
+
+def view_nchw(t):
+    """View of a contiguous [B, C, *spatial] tensor."""
+    if t is None:
+        return NULL_VIEW
+    B, Cc = t.shape[0], t.shape[1]
+    P = t[0, 0].numel()
+    return View(t.data_ptr(), Cc * P, P, 1)
+
+
+def launch_count():
+    return int(lib().icm_launch_count())

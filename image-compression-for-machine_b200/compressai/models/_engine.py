@@ -1,0 +1,168 @@
+"""Host-side driver of the CUDA transform kernels: weight packing and thin call wrappers.
+
+Activations are channels-last.  `conv()` runs csrc/conv.cu (tcgen05 implicit GEMM) for nn.Conv2d / nn.Linear
+parameter holders; `swin_block()` etc. string the kernels of csrc/transforms.cu together.  PyTorch supplies
+device memory and the stream; no torch operator does arithmetic on this path.
+"""
+import ctypes as C
+
+import torch
+
+from compressai import _native
+from compressai._native import ACT_GELU, ACT_NONE, OUT_BF16, OUT_F32, ConvArgs, NativeError, check, lib, stream_ptr
+
+
+class PackedConv:
+    """bf16 [Cout_pad, KH*KW*Cin_pad] weight + fp32 bias on the device (icm_pack_conv_weight)."""
+
+    __slots__ = ("w", "bias", "Cin", "Cout", "KH", "KW", "stride", "pad", "ps")
+
+    def __init__(self, weight, bias, stride=1, pad=0, ps=0):
+        w = weight.detach().float().contiguous()
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        self.Cout, self.Cin, self.KH, self.KW = w.shape
+        self.stride, self.pad, self.ps = int(stride), int(pad), int(ps)
+        cin_pad = (self.Cin + 63) // 64 * 64
+        cout_pad = (self.Cout + 15) // 16 * 16
+        self.w = torch.empty((cout_pad, self.KH * self.KW * cin_pad), dtype=torch.bfloat16, device=w.device)
+        check(lib().icm_pack_conv_weight(w.data_ptr(), self.Cout, self.Cin, self.KH, self.KW, cin_pad, cout_pad, self.ps,
+                                         self.w.data_ptr(), stream_ptr()), "icm_pack_conv_weight")
+        self.bias = None if bias is None else bias.detach().float().contiguous().clone()
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self._packed = {}
+
+    def invalidate(self):
+        self._packed.clear()
+
+    # ---------------------------------------------------------------------------------- weights
+    def packed(self, module, ps=0):
+        key = (id(module), ps)
+        pk = self._packed.get(key)
+        if pk is None:
+            if isinstance(module, torch.nn.Conv2d):
+                pk = PackedConv(module.weight, module.bias, module.stride[0], module.padding[0], ps)
+            elif isinstance(module, torch.nn.Linear):
+                pk = PackedConv(module.weight, module.bias, 1, 0, ps)
+            else:
+                raise TypeError(type(module))
+            self._packed[key] = pk
+        return pk
+
+    def f32(self, p):
+        key = (id(p), "f32")
+        t = self._packed.get(key)
+        if t is None:
+            t = p.detach().float().contiguous()
+            self._packed[key] = t
+        return t
+
+    # ---------------------------------------------------------------------------------- kernels
+    def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None):
+        """x: bf16 [.., pitch] channels-last holding B*H*W pixels.  Returns the output tensor
+        ([B*Ho*Wo(*r*r), Cout(/r^2)] unless `out` is given, then writes channels [out_offset, +Cout) of it)."""
+        assert x.dtype == torch.bfloat16 and x.is_cuda
+        in_pitch = x.shape[-1]
+        cin = pk.Cin if cin is None else cin
+        if cin != pk.Cin:
+            raise NativeError(f"conv: input channels {cin} != weight channels {pk.Cin}")
+        Ho = (H + 2 * pk.pad - pk.KH) // pk.stride + 1
+        Wo = (W + 2 * pk.pad - pk.KW) // pk.stride + 1
+        r = pk.ps if pk.ps else 1
+        cout_eff = pk.Cout // (r * r)
+        if out is None:
+            out = torch.empty((B * Ho * r * Wo * r, cout_eff), dtype=torch.float32 if out_dtype == OUT_F32 else torch.bfloat16, device=x.device)
+        a = ConvArgs()
+        a.inp, a.weight = x.data_ptr(), pk.w.data_ptr()
+        a.bias = pk.bias.data_ptr() if pk.bias is not None else None
+        a.out = out.data_ptr() + out_offset * out.element_size()
+        a.residual = residual.data_ptr() if residual is not None else None
+        a.B, a.H, a.W, a.Cin, a.in_pitch = B, H, W, cin, in_pitch
+        a.Cout, a.out_pitch = pk.Cout, out.shape[-1]
+        a.KH, a.KW, a.stride, a.pad = pk.KH, pk.KW, pk.stride, pk.pad
+        a.act, a.out_dtype, a.pixel_shuffle = act, out_dtype, pk.ps
+        a.res_pitch = residual.shape[-1] if residual is not None else 0
+        check(lib().icm_conv2d(C.byref(a), stream_ptr()), "icm_conv2d")
+        return out
+
+    def linear(self, x, pk, **kw):
+        """x: bf16 [M, K] -> [M, N]."""
+        return self.conv(x, 1, 1, x.shape[0], pk, **kw)
+
+    def layernorm(self, x, norm, out_dtype=OUT_BF16, gather=None):
+        """x fp32 [rows, C]; gather=(B,H,W): PatchMerging gather, output [B*ceil(H/2)*ceil(W/2), 4C]."""
+        Cc = norm.normalized_shape[0]
+        if gather is None:
+            rows, B, H, W, g = x.shape[0], 0, 0, 0, 0
+        else:
+            B, H, W = gather
+            rows, g = B * ((H + 1) // 2) * ((W + 1) // 2), 1
+        out = torch.empty((rows, Cc), dtype=torch.bfloat16 if out_dtype == OUT_BF16 else torch.float32, device=x.device)
+        check(lib().icm_layernorm(x.data_ptr(), self.f32(norm.weight).data_ptr(), self.f32(norm.bias).data_ptr(), out.data_ptr(),
+                                  out_dtype, rows, Cc, g, B, H, W, stream_ptr()), "icm_layernorm")
+        return out
+
+    def cast_bf16(self, x):
+        rows, Cc = x.shape
+        out = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
+        check(lib().icm_cast_bf16(x.data_ptr(), rows, Cc, Cc, out.data_ptr(), Cc, stream_ptr()), "icm_cast_bf16")
+        return out
+
+    def window_attention(self, qkv, B, H, W, Cc, heads, window, shift, bias_table):
+        out = torch.empty((B * H * W, Cc), dtype=torch.bfloat16, device=qkv.device)
+        check(lib().icm_window_attention(qkv.data_ptr(), out.data_ptr(), self.f32(bias_table).data_ptr(), B, H, W, Cc, heads,
+                                         window, shift, stream_ptr()), "icm_window_attention")
+        return out
+
+    # ---------------------------------------------------------------------------------- Swin pieces
+    def swin_block(self, x, B, H, W, blk, shifted):
+        """x: fp32 tokens [B*H*W, C], updated in place (stf.py:149-199)."""
+        Cc = x.shape[1]
+        xn = self.layernorm(x, blk.norm1)
+        qkv = self.linear(xn, self.packed(blk.attn.qkv))
+        ao = self.window_attention(qkv, B, H, W, Cc, blk.attn.num_heads, blk.window_size, blk.window_size // 2 if shifted else 0,
+                                   blk.attn.relative_position_bias_table)
+        self.linear(ao, self.packed(blk.attn.proj), out=x, out_dtype=OUT_F32, residual=x)
+        xn = self.layernorm(x, blk.norm2)
+        h = self.linear(xn, self.packed(blk.mlp.fc1), act=ACT_GELU)
+        self.linear(h, self.packed(blk.mlp.fc2), out=x, out_dtype=OUT_F32, residual=x)
+        return x
+
+    def stage(self, x, B, H, W, layer):
+        for i, blk in enumerate(layer.blocks):
+            x = self.swin_block(x, B, H, W, blk, i % 2 == 1)
+        ds = layer.downsample
+        if ds is None:
+            return x, H, W
+        if ds.kind == "merge":
+            xn = self.layernorm(x, ds.norm, gather=(B, H, W))
+            x = self.linear(xn, self.packed(ds.reduction), out_dtype=OUT_F32)
+            return x, (H + 1) // 2, (W + 1) // 2
+        xn = self.layernorm(x, ds.norm)
+        x = self.conv(xn, B, H, W, self.packed(ds.reduction, ps=2), out_dtype=OUT_F32)
+        return x, 2 * H, 2 * W
+
+    def conv_stack(self, x, B, H, W, seq, final_dtype=OUT_F32, final_act=ACT_NONE, final_out=None, cin=None):
+        """nn.Sequential of Conv2d / GELU / (Conv2d + PixelShuffle) holders (stf.py:474-546)."""
+        convs = []
+        for m in seq:
+            if isinstance(m, torch.nn.Conv2d):
+                convs.append((m, 0))
+            elif isinstance(m, torch.nn.Sequential):  # subpel_conv3x3
+                convs.append((m[0], m[1].upscale_factor))
+        for k, (m, ps) in enumerate(convs):
+            last = k == len(convs) - 1
+            pk = self.packed(m, ps)
+            if last:
+                x = self.conv(x, B, H, W, pk, out=final_out, act=final_act, out_dtype=final_dtype, cin=cin if k == 0 else None)
+            else:
+                x = self.conv(x, B, H, W, pk, act=ACT_GELU, cin=cin if k == 0 else None)
+            H = (H + 2 * pk.pad - pk.KH) // pk.stride + 1
+            W = (W + 2 * pk.pad - pk.KW) // pk.stride + 1
+            if ps:
+                H, W = H * ps, W * ps
+        return x, H, W

@@ -1,0 +1,53 @@
+// Shared helpers for the icm_b200 CUDA library (error plumbing, launch accounting, strided views).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "icm_b200.h"
+
+namespace icm {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define ICM_CHECK_ARG(cond, ...)                    \
+    do {                                            \
+        if (!(cond)) {                              \
+            ::icm::set_error(__VA_ARGS__);          \
+            return ICM_ERR_INVALID_ARG;             \
+        }                                           \
+    } while (0)
+
+#define ICM_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::icm::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return ICM_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define ICM_LAUNCH_CHECK()                                                                      \
+    do {                                                                                        \
+        ::icm::count_launch();                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess) {                                                               \
+            ::icm::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return ICM_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// device-side strided [B, C, P] view
+struct View {
+    char *ptr;
+    long long sb, sc, sp;
+};
+static inline View as_view(const icm_view &v) { return View{(char *)v.ptr, v.sb, v.sc, v.sp}; }
+
+int sm_count();
+
+}  // namespace icm

@@ -1,0 +1,431 @@
+// Implicit-GEMM convolution / linear layer on the Blackwell tensor cores (rows T3-T11 of SURVEY.md §8a).
+//
+//   D[pixel, cout] = act( sum_{tap, cin} A[pixel + tap, cin] * W[cout, tap, cin] + bias ) (+ residual)
+//
+// One CTA computes a 128-pixel x BN-channel output tile:
+//   warp 0     TMA producer: per k-step one 4-D box of the channels-last activation
+//              (64 channels x TW x TH pixels, shifted by the filter tap; the zero padding of the convolution
+//              is TMA's out-of-bounds zero fill, stride-2 convolutions use the tensor map's element strides)
+//              and one 2-D box of the packed weights, both landing 128B-swizzled in shared memory;
+//   warp 1     allocates TMEM and issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM);
+//   warps 2-5  epilogue: tcgen05.ld the accumulator rows, bias + activation (+ residual) in registers,
+//              vectorised stores (optionally with the PixelShuffle permutation folded into the address).
+// The K loop order (tap-major, then 64-channel chunks) is fixed and there is no split-K, so every output
+// element is reduced in the same order whatever the batch size or tile shape: the encoder and decoder
+// sides of the codec see bit-identical means/scales (SURVEY.md §7 "Encoder/decoder determinism").
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace icm {
+
+constexpr int BM = 128;      // pixels per tile == TMEM lanes
+constexpr int BK = 64;       // bf16 channels per k-step == one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int MAX_STAGES = 6;
+
+// ---------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{ // implies tcgen05.fence::before_thread_sync
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct ConvParams {
+    int Ho, Wo;            // output spatial size
+    int TW_log2;           // tile = TW x TH pixels, TW * TH == 128
+    int tiles_w, tiles_h;
+    int k_chunks;          // ceil(Cin / 64)
+    int Cin_pad;           // channels per tap in the packed weight
+    int KH, KW, stride, pad;
+    int BN, Cout, stages, tmem_cols;
+    int act, out_dtype, pixel_shuffle;
+    long long out_pitch, res_pitch;
+    const float *bias;
+    const float *residual;
+    void *out;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act)
+{
+    if (act == ICM_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    if (act == ICM_ACT_HALF_TANH) return 0.5f * tanhf(v);
+    if (act == ICM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    return v;
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // layout: [stages][A 16 KB][B BN*128 B] | barriers | tmem slot
+    const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2;
+    const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tiles + (size_t)p.stages * stage_bytes);
+    uint64_t *empty_bar = full_bar + MAX_STAGES;
+    uint64_t *accum_bar = empty_bar + MAX_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int tile = blockIdx.x;
+    const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+    const int b = tile;
+    const int TW = 1 << p.TW_log2, TH = BM >> p.TW_log2;
+    const int w0 = tw_i * TW, h0 = th_i * TH;
+    const int n0 = blockIdx.y * p.BN;
+    const int k_iters = p.KH * p.KW * p.k_chunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) { // TMEM allocation is warp-collective
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < k_iters; ++it) {
+                const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
+                const int dy = tap / p.KW, dx = tap - dy * p.KW;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char *sa = tiles + (size_t)stage * stage_bytes;
+                unsigned char *sb = sa + a_bytes;
+                mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                tma_load_4d(&map_a, &full_bar[stage], sa, chunk * BK, w0 * p.stride + dx - p.pad, h0 * p.stride + dy - p.pad, b);
+                tma_load_2d(&map_w, &full_bar[stage], sb, tap * p.Cin_pad + chunk * BK, n0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < k_iters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
+                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the 16-byte address field
+                    umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+                if (it == k_iters - 1) umma_commit(accum_bar); // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3; // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;
+        const int th = r >> p.TW_log2, tw = r & (TW - 1);
+        const int oh = h0 + th, ow = w0 + tw;
+        const bool valid = (oh < p.Ho) && (ow < p.Wo);
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
+        const int Cq = p.pixel_shuffle ? p.Cout / (p.pixel_shuffle * p.pixel_shuffle) : 0;
+        for (int c16 = 0; c16 < p.BN / 16; ++c16) {
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c16 * 16), acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int n = n0 + c16 * 16;
+            if (!valid || n >= p.Cout) continue;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+            if (p.bias) {
+                const float4 *bp = reinterpret_cast<const float4 *>(p.bias + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float4 t = __ldg(bp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+            long long off;
+            if (p.pixel_shuffle) {
+                const int rr = p.pixel_shuffle;
+                const int quad = n / Cq, c = n - quad * Cq;
+                const int i = quad / rr, jj = quad - i * rr;
+                off = (((long long)b * p.Ho * rr + (long long)oh * rr + i) * ((long long)p.Wo * rr) + (long long)ow * rr + jj) * p.out_pitch + c;
+            } else {
+                off = pix * p.out_pitch + n;
+            }
+            if (p.residual) {
+                const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix * p.res_pitch + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float4 t = __ldg(rp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+            }
+            if (p.out_dtype == ICM_OUT_F32) {
+                float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                }
+                uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + off);
+                op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ weight packing
+// OIHW fp32 -> bf16 [Cout_pad][KH*KW][Cin_pad]; with pixel_shuffle = r the output channels are permuted so
+// that GEMM column (i*r + j) * (Cout / r^2) + c holds conv channel c*r^2 + i*r + j (nn.PixelShuffle order).
+__global__ void pack_weight_kernel(const float *__restrict__ w, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,
+                                   int ps, __nv_bfloat16 *__restrict__ out)
+{
+    const long long total = (long long)Cout_pad * KH * KW * Cin_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin_pad);
+        long long t = i / Cin_pad;
+        const int tap = (int)(t % (KH * KW));
+        const int n = (int)(t / (KH * KW));
+        float v = 0.f;
+        if (n < Cout && ci < Cin) {
+            int co = n;
+            if (ps > 1) {
+                const int Cq = Cout / (ps * ps);
+                const int quad = n / Cq, c = n - quad * Cq;
+                co = c * ps * ps + quad;
+            }
+            v = w[((long long)co * Cin + ci) * KH * KW + tap];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int pick_tile_w_log2(int Ho, int Wo)
+{
+    long long best = -1;
+    int best_l = 7;
+    for (int l = 7; l >= 3; --l) {
+        const int TW = 1 << l, TH = BM >> l;
+        const long long covered = (long long)((Wo + TW - 1) / TW) * TW * ((Ho + TH - 1) / TH) * TH;
+        if (best < 0 || covered < best) { best = covered; best_l = l; }
+    }
+    return best_l;
+}
+
+}  // namespace icm
+
+using namespace icm;
+
+extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
+{
+    ICM_CHECK_ARG(a && a->in && a->weight && a->out, "icm_conv2d: null argument");
+    ICM_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "icm_conv2d: empty input");
+    ICM_CHECK_ARG(a->Cin > 0 && a->Cin <= a->in_pitch && a->in_pitch % 8 == 0, "icm_conv2d: Cin=%d in_pitch=%d (pitch must be a multiple of 8 and >= Cin)", a->Cin, a->in_pitch);
+    ICM_CHECK_ARG(a->Cout > 0 && a->Cout % 16 == 0, "icm_conv2d: Cout=%d must be a multiple of 16", a->Cout);
+    ICM_CHECK_ARG(a->KH >= 1 && a->KW >= 1 && a->stride >= 1 && a->stride <= 2 && a->pad >= 0, "icm_conv2d: bad filter geometry");
+    ICM_CHECK_ARG(((uintptr_t)a->in & 15) == 0 && ((uintptr_t)a->weight & 15) == 0 && ((uintptr_t)a->out & 15) == 0, "icm_conv2d: pointers must be 16-byte aligned");
+    const int ps = a->pixel_shuffle;
+    ICM_CHECK_ARG(ps == 0 || (ps >= 2 && a->Cout % (ps * ps) == 0 && (a->Cout / (ps * ps)) % 16 == 0), "icm_conv2d: pixel_shuffle=%d incompatible with Cout=%d", ps, a->Cout);
+    ICM_CHECK_ARG(ps == 0 || a->residual == nullptr, "icm_conv2d: residual with pixel_shuffle is unsupported");
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("icm_conv2d: cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return ICM_ERR_NO_DEVICE; }
+
+    ConvParams p{};
+    p.Ho = (a->H + 2 * a->pad - a->KH) / a->stride + 1;
+    p.Wo = (a->W + 2 * a->pad - a->KW) / a->stride + 1;
+    ICM_CHECK_ARG(p.Ho > 0 && p.Wo > 0, "icm_conv2d: empty output");
+    p.TW_log2 = pick_tile_w_log2(p.Ho, p.Wo);
+    const int TW = 1 << p.TW_log2, TH = BM >> p.TW_log2;
+    p.tiles_w = (p.Wo + TW - 1) / TW;
+    p.tiles_h = (p.Ho + TH - 1) / TH;
+    const int Cin = a->Cin; // channels actually read; the packed weight pads each tap to a multiple of 64
+    p.k_chunks = (Cin + BK - 1) / BK;
+    p.Cin_pad = p.k_chunks * BK;
+    p.KH = a->KH; p.KW = a->KW; p.stride = a->stride; p.pad = a->pad;
+    p.Cout = a->Cout;
+    const int n_tiles = (a->Cout + 255) / 256;
+    p.BN = ((a->Cout + n_tiles - 1) / n_tiles + 15) & ~15;
+    // small problems: more, narrower N tiles so that more SMs take part
+    const long long m_tiles = (long long)a->B * p.tiles_w * p.tiles_h;
+    while (p.BN > 64 && p.BN % 32 == 0 && m_tiles * ((a->Cout + p.BN - 1) / p.BN) * 2 <= sm_count()) p.BN /= 2;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.BN) p.tmem_cols *= 2;
+    const int k_iters = p.KH * p.KW * p.k_chunks;
+    const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2;
+    const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+    p.stages = (int)((200 * 1024) / stage_bytes);
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    if (p.stages > k_iters) p.stages = k_iters;
+    if (p.stages < 1) p.stages = 1;
+    p.act = a->act; p.out_dtype = a->out_dtype; p.pixel_shuffle = ps;
+    p.out_pitch = a->out_pitch; p.res_pitch = a->res_pitch;
+    p.bias = a->bias; p.residual = a->residual; p.out = a->out;
+    ICM_CHECK_ARG(a->out_pitch % (a->out_dtype == ICM_OUT_F32 ? 4 : 8) == 0, "icm_conv2d: out_pitch=%d breaks 16-byte store alignment", a->out_pitch);
+    ICM_CHECK_ARG(!a->residual || (a->res_pitch % 4 == 0 && ((uintptr_t)a->residual & 15) == 0), "icm_conv2d: residual must be 16-byte aligned");
+    ICM_CHECK_ARG(!a->bias || ((uintptr_t)a->bias & 15) == 0, "icm_conv2d: bias must be 16-byte aligned");
+
+    CUtensorMap map_a, map_w;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t strides[3] = {(cuuint64_t)a->in_pitch * 2, (cuuint64_t)a->W * a->in_pitch * 2, (cuuint64_t)a->H * a->W * a->in_pitch * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)((TW - 1) * a->stride + 1), (cuuint32_t)((TH - 1) * a->stride + 1), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a->in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("icm_conv2d: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return ICM_ERR_CUDA; }
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)p.KH * p.KW * p.Cin_pad;
+        const int cout_pad = (a->Cout + 15) & ~15;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)cout_pad};
+        cuuint64_t strides[1] = {ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p.BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(a->weight), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("icm_conv2d: cuTensorMapEncodeTiled(W) failed (%d)", (int)r); return ICM_ERR_CUDA; }
+    }
+    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 1) * 8 + 16;
+    static thread_local size_t configured = 0;
+    if (smem_bytes > configured) {
+        ICM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = 227 * 1024;
+    }
+    ICM_CHECK_ARG(m_tiles <= 0x7FFFFFFF, "icm_conv2d: too many tiles");
+    dim3 grid((unsigned)m_tiles, (a->Cout + p.BN - 1) / p.BN);
+    conv_igemm_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_pack_conv_weight(const float *d_w_oihw, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,
+                                    int pixel_shuffle, void *d_out_bf16, void *stream)
+{
+    ICM_CHECK_ARG(d_w_oihw && d_out_bf16, "icm_pack_conv_weight: null argument");
+    ICM_CHECK_ARG(Cin_pad >= Cin && Cin_pad % 64 == 0 && Cout_pad >= Cout, "icm_pack_conv_weight: bad padding");
+    const long long total = (long long)Cout_pad * KH * KW * Cin_pad;
+    const int grid = (int)min((total + 255) / 256, (long long)sm_count() * 8);
+    pack_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_w_oihw, Cout, Cin, KH, KW, Cin_pad, Cout_pad, pixel_shuffle,
+                                                           reinterpret_cast<__nv_bfloat16 *>(d_out_bf16));
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}

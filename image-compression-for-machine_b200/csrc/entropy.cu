@@ -1,0 +1,384 @@
+// Entropy-model step on the device (rows E1-E6, E9 of SURVEY.md §8a): fused, HBM-bound elementwise
+// kernels.  One pass reads (y, mu, scale) and writes everything the next stage needs -- int32 symbols and
+// CDF indexes already in the coder's stream order, ŷ in fp32, and ŷ in bf16 straight into the channel
+// slots of the context-model support buffers -- instead of the reference's ~70 elementwise launches per
+// slice (63 compare/subtract passes in build_indexes alone, entropy_models.py:661-666).
+//
+// All tensors are strided [B, C, P] views so the same kernel serves NCHW (the reference's layout, used by
+// the drop-in nn.Module API) and channels-last (the layout of the conv kernels).  A CTA owns a 32-channel
+// x 32-pixel tile; every tensor is touched with its own unit-stride dimension on the fast thread index
+// and layout changes happen through a padded shared-memory tile, so loads and stores are 128-byte
+// coalesced on both sides.
+#include "common.cuh"
+
+#include <type_traits>
+
+namespace icm {
+
+constexpr int TILE = 32;
+constexpr int THREADS = 256;
+constexpr int PER_THREAD = TILE * TILE / THREADS; // 4
+
+struct TileCoord {
+    int b, c0;
+    long long p0;
+    int nc, np; // valid extent of this tile
+};
+
+// element k (0..3) of thread t inside the tile, for a tensor whose fast dimension is channels / pixels
+__device__ __forceinline__ void elem_cfast(int t, int k, int &ci, int &pi) { ci = t & 31; pi = (t >> 5) + 8 * k; }
+__device__ __forceinline__ void elem_pfast(int t, int k, int &ci, int &pi) { pi = t & 31; ci = (t >> 5) + 8 * k; }
+
+template <typename T>
+__device__ __forceinline__ void load_tile(const View &v, const TileCoord &tc, float (*tile)[TILE + 1])
+{
+    if (!v.ptr) { // absent optional input (e.g. no means): reads as zero
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) { int ci, pi; elem_pfast(threadIdx.x, k, ci, pi); tile[ci][pi] = 0.f; }
+        return;
+    }
+    const T *base = reinterpret_cast<const T *>(v.ptr) + (long long)tc.b * v.sb;
+    const bool cfast = (v.sc == 1);
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        int ci, pi;
+        if (cfast) elem_cfast(threadIdx.x, k, ci, pi); else elem_pfast(threadIdx.x, k, ci, pi);
+        if (ci < tc.nc && pi < tc.np) {
+            T val = base[(long long)(tc.c0 + ci) * v.sc + (tc.p0 + pi) * v.sp];
+            if constexpr (std::is_same<T, int32_t>::value) tile[ci][pi] = __int_as_float(val);
+            else tile[ci][pi] = (float)val;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_tile(const View &v, const TileCoord &tc, float (*tile)[TILE + 1])
+{
+    if (!v.ptr) return;
+    T *base = reinterpret_cast<T *>(v.ptr) + (long long)tc.b * v.sb;
+    const bool cfast = (v.sc == 1);
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        int ci, pi;
+        if (cfast) elem_cfast(threadIdx.x, k, ci, pi); else elem_pfast(threadIdx.x, k, ci, pi);
+        if (ci < tc.nc && pi < tc.np) {
+            const float f = tile[ci][pi];
+            T *dst = base + (long long)(tc.c0 + ci) * v.sc + (tc.p0 + pi) * v.sp;
+            if constexpr (std::is_same<T, int32_t>::value) *dst = __float_as_int(f);
+            else if constexpr (std::is_same<T, __nv_bfloat16>::value) *dst = __float2bfloat16_rn(f);
+            else *dst = f;
+        }
+    }
+}
+
+__device__ __forceinline__ TileCoord tile_coord(int C, long long P)
+{
+    TileCoord tc;
+    tc.p0 = (long long)blockIdx.x * TILE;
+    tc.c0 = blockIdx.y * TILE;
+    tc.b = blockIdx.z;
+    tc.nc = min(TILE, C - tc.c0);
+    tc.np = (int)min((long long)TILE, P - tc.p0);
+    return tc;
+}
+
+// idx = (n-1) - #{j < n-1 : s <= table[j]} == first j in [0, n-1) with s <= table[j], else n-1
+// (entropy_models.py:661-666); a NaN scale compares false everywhere and lands on n-1 like the reference.
+__device__ __forceinline__ int bucket_index(float s, const float *table, int n)
+{
+    int lo = 0, hi = n - 1; // answer in [lo, hi]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s <= table[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ float lower_bound_f(float x, float b)
+{ // torch.max(x, bound): NaN propagates
+    return (x != x) ? x : fmaxf(x, b);
+}
+
+__device__ __forceinline__ float std_cumulative(float v)
+{ // entropy_models.py:578-582
+    return 0.5f * erfcf(-0.70710678118654752440f * v);
+}
+
+enum GcMode { GC_QUANT = 0, GC_INDEX = 1, GC_DEQUANT = 2, GC_LIK = 3, GC_ADD = 4 };
+
+struct GcArgs {
+    View y, mu, scale;          // fp32 inputs (GC_DEQUANT: y is the int32 symbol view; GC_ADD: y = lrp)
+    View sym, idx;              // int32 outputs
+    View yhat, lik, bf_a, bf_b; // fp32, fp32, bf16, bf16 outputs (GC_ADD: yhat is read-modify-write)
+    const float *table;
+    int n_levels;
+    float scale_bound, lik_bound;
+    int C;
+    long long P;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) gc_kernel(GcArgs a)
+{
+    __shared__ float t0[TILE][TILE + 1], t1[TILE][TILE + 1], t2[TILE][TILE + 1];
+    __shared__ float s_table[256];
+    const TileCoord tc = tile_coord(a.C, a.P);
+    if ((MODE == GC_QUANT || MODE == GC_INDEX) && a.table)
+        for (int i = threadIdx.x; i < a.n_levels; i += THREADS) s_table[i] = a.table[i];
+    if (MODE == GC_QUANT || MODE == GC_LIK) { load_tile<float>(a.y, tc, t0); load_tile<float>(a.mu, tc, t1); load_tile<float>(a.scale, tc, t2); }
+    if (MODE == GC_INDEX) load_tile<float>(a.scale, tc, t2);
+    if (MODE == GC_DEQUANT) { load_tile<int32_t>(a.y, tc, t0); load_tile<float>(a.mu, tc, t1); }
+    if (MODE == GC_ADD) { load_tile<float>(a.yhat, tc, t0); load_tile<float>(a.y, tc, t1); }
+    __syncthreads();
+    // every thread transforms the 4 tile cells it owns (cell ownership is arbitrary once in smem)
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        int ci, pi;
+        elem_pfast(threadIdx.x, k, ci, pi);
+        if (MODE == GC_QUANT) {
+            const float y = t0[ci][pi], mu = t1[ci][pi], sc = t2[ci][pi];
+            const float r = rintf(y - mu); // torch.round: half to even
+            const int q = (int)r;
+            const int id = a.table ? bucket_index(lower_bound_f(sc, a.scale_bound), s_table, a.n_levels) : 0;
+            t0[ci][pi] = __int_as_float(q);
+            t2[ci][pi] = __int_as_float(id);
+            t1[ci][pi] = (float)q + mu; // y_q_slice + mu (stf.py:716)
+        } else if (MODE == GC_INDEX) {
+            t2[ci][pi] = __int_as_float(bucket_index(lower_bound_f(t2[ci][pi], a.scale_bound), s_table, a.n_levels));
+        } else if (MODE == GC_DEQUANT) {
+            t1[ci][pi] = (float)__float_as_int(t0[ci][pi]) + t1[ci][pi];
+        } else if (MODE == GC_LIK) {
+            const float y = t0[ci][pi], mu = t1[ci][pi];
+            const float s = lower_bound_f(t2[ci][pi], a.scale_bound);
+            const float yh = rintf(y - mu) + mu;         // quantize(..., "dequantize", means)
+            const float v = fabsf(yh - mu);              // values = |outputs - means|
+            const float up = std_cumulative((0.5f - v) / s);
+            const float lo = std_cumulative((-0.5f - v) / s);
+            t1[ci][pi] = yh;
+            t0[ci][pi] = lower_bound_f(up - lo, a.lik_bound);
+        } else if (MODE == GC_ADD) {
+            t1[ci][pi] = t0[ci][pi] + t1[ci][pi];
+        }
+    }
+    __syncthreads();
+    if (MODE == GC_QUANT) { store_tile<int32_t>(a.sym, tc, t0); store_tile<int32_t>(a.idx, tc, t2); }
+    if (MODE == GC_INDEX) store_tile<int32_t>(a.idx, tc, t2);
+    if (MODE == GC_LIK) store_tile<float>(a.lik, tc, t0);
+    store_tile<float>(a.yhat, tc, t1);
+    store_tile<__nv_bfloat16>(a.bf_a, tc, t1);
+    store_tile<__nv_bfloat16>(a.bf_b, tc, t1);
+}
+
+template <int MODE>
+static int launch_gc(const GcArgs &a, int B, void *stream)
+{
+    ICM_CHECK_ARG(B > 0 && a.C > 0 && a.P > 0, "entropy kernel: empty tensor (B=%d C=%d P=%lld)", B, a.C, a.P);
+    ICM_CHECK_ARG(B <= 65535 && (a.C + TILE - 1) / TILE <= 65535, "entropy kernel: B or C too large");
+    dim3 grid((unsigned)((a.P + TILE - 1) / TILE), (a.C + TILE - 1) / TILE, B);
+    gc_kernel<MODE><<<grid, THREADS, 0, as_stream(stream)>>>(a);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+static View stream_view(int32_t *p, long long stream_stride, long long stream_offset, long long P)
+{
+    return View{(char *)(p ? p + stream_offset : nullptr), stream_stride, P, 1};
+}
+
+// ------------------------------------------------------------------------------------------------
+// EntropyBottleneck: per-channel 1-3-3-3-3-1 scalar network (entropy_models.py:400-433)
+constexpr int EBP = ICM_EB_PARAMS_PER_CHANNEL;
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// p: transformed parameters of one channel (softplus(matrix), bias, tanh(factor))
+__device__ __forceinline__ float eb_logits(const float *p, float v)
+{
+    float h[3], g[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        h[j] = p[j] * v + p[3 + j];
+        h[j] += p[6 + j] * tanhf(h[j]);
+    }
+    const float *q = p + 9;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float acc = q[j * 3 + 0] * h[0];
+            acc += q[j * 3 + 1] * h[1];
+            acc += q[j * 3 + 2] * h[2];
+            acc += q[9 + j];
+            g[j] = acc + q[12 + j] * tanhf(acc);
+        }
+        h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
+        q += 15;
+    }
+    float out = q[0] * h[0];
+    out += q[1] * h[1];
+    out += q[2] * h[2];
+    return out + q[3];
+}
+
+struct EbArgs {
+    View z, sym, idx, zhat, zhat_bf, lik;
+    const float *params;
+    float lik_bound;
+    int C;
+    long long P;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) eb_kernel(EbArgs a)
+{
+    __shared__ float t0[TILE][TILE + 1], t1[TILE][TILE + 1];
+    __shared__ float s_par[TILE][EBP + 1];
+    const TileCoord tc = tile_coord(a.C, a.P);
+    for (int i = threadIdx.x; i < tc.nc * EBP; i += THREADS) {
+        const int c = i / EBP, k = i % EBP;
+        float v = a.params[(size_t)(tc.c0 + c) * EBP + k];
+        // positions of matrices / factors inside the 59-float record
+        const bool is_matrix = (k < 3) || (k >= 9 && k < 18) || (k >= 24 && k < 33) || (k >= 39 && k < 48) || (k >= 54 && k < 57);
+        const bool is_factor = (k >= 6 && k < 9) || (k >= 21 && k < 24) || (k >= 36 && k < 39) || (k >= 51 && k < 54);
+        if (MODE == 1) { if (is_matrix) v = softplus_f(v); else if (is_factor) v = tanhf(v); }
+        s_par[c][k] = v;
+    }
+    if (MODE == 2) load_tile<int32_t>(a.sym, tc, t0); else load_tile<float>(a.z, tc, t0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        int ci, pi;
+        elem_pfast(threadIdx.x, k, ci, pi);
+        if (ci >= tc.nc) continue;
+        const float med = s_par[ci][EBP - 1];
+        if (MODE == 0) {
+            const int q = (int)rintf(t0[ci][pi] - med);
+            t0[ci][pi] = __int_as_float(q);
+            t1[ci][pi] = (float)q + med;
+        } else if (MODE == 2) {
+            t1[ci][pi] = (float)__float_as_int(t0[ci][pi]) + med;
+        } else {
+            const float zh = rintf(t0[ci][pi] - med) + med;
+            const float lo = eb_logits(s_par[ci], zh - 0.5f);
+            const float up = eb_logits(s_par[ci], zh + 0.5f);
+            const float sum = lo + up;
+            const float sign = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f); // -torch.sign(lo + up)
+            const float l = fabsf(sigmoid_f(sign * up) - sigmoid_f(sign * lo));
+            t1[ci][pi] = zh;
+            t0[ci][pi] = lower_bound_f(l, a.lik_bound);
+        }
+    }
+    __syncthreads();
+    if (MODE == 0) {
+        store_tile<int32_t>(a.sym, tc, t0);
+        if (a.idx.ptr) { // index = channel id (entropy_models.py:492-502)
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < PER_THREAD; ++k) {
+                int ci, pi;
+                elem_pfast(threadIdx.x, k, ci, pi);
+                t0[ci][pi] = __int_as_float(tc.c0 + ci);
+            }
+            __syncthreads();
+            store_tile<int32_t>(a.idx, tc, t0);
+        }
+    }
+    if (MODE == 1) store_tile<float>(a.lik, tc, t0);
+    store_tile<float>(a.zhat, tc, t1);
+    store_tile<__nv_bfloat16>(a.zhat_bf, tc, t1);
+}
+
+}  // namespace icm
+
+using namespace icm;
+
+extern "C" int icm_gc_quantize_index(icm_view y, icm_view mu, icm_view scale, int B, int C, int64_t P,
+                                     const float *d_scale_table, int n_levels, float scale_bound,
+                                     int32_t *d_symbols, int32_t *d_indexes, int64_t stream_stride, int64_t stream_offset,
+                                     icm_view y_hat_f32, icm_view y_hat_bf16_a, icm_view y_hat_bf16_b, void *stream)
+{
+    ICM_CHECK_ARG(y.ptr && d_symbols, "icm_gc_quantize_index: null argument");
+    ICM_CHECK_ARG(!scale.ptr == !d_indexes, "icm_gc_quantize_index: scale and indexes go together");
+    ICM_CHECK_ARG(!scale.ptr || (d_scale_table && n_levels >= 1 && n_levels <= 256), "icm_gc_quantize_index: n_levels=%d outside [1,256]", n_levels);
+    GcArgs a{};
+    a.y = as_view(y); a.mu = as_view(mu); a.scale = as_view(scale);
+    a.sym = stream_view(d_symbols, stream_stride, stream_offset, P);
+    a.idx = stream_view(d_indexes, stream_stride, stream_offset, P);
+    a.yhat = as_view(y_hat_f32); a.bf_a = as_view(y_hat_bf16_a); a.bf_b = as_view(y_hat_bf16_b);
+    a.table = d_scale_table; a.n_levels = n_levels; a.scale_bound = scale_bound; a.C = C; a.P = P;
+    return launch_gc<GC_QUANT>(a, B, stream);
+}
+
+extern "C" int icm_gc_build_indexes(icm_view scale, int B, int C, int64_t P, const float *d_scale_table, int n_levels,
+                                    float scale_bound, int32_t *d_indexes, int64_t stream_stride, int64_t stream_offset,
+                                    void *stream)
+{
+    ICM_CHECK_ARG(scale.ptr && d_scale_table && d_indexes, "icm_gc_build_indexes: null argument");
+    ICM_CHECK_ARG(n_levels >= 1 && n_levels <= 256, "icm_gc_build_indexes: n_levels=%d outside [1,256]", n_levels);
+    GcArgs a{};
+    a.scale = as_view(scale);
+    a.idx = stream_view(d_indexes, stream_stride, stream_offset, P);
+    a.table = d_scale_table; a.n_levels = n_levels; a.scale_bound = scale_bound; a.C = C; a.P = P;
+    return launch_gc<GC_INDEX>(a, B, stream);
+}
+
+extern "C" int icm_gc_dequantize(const int32_t *d_symbols, int64_t stream_stride, int64_t stream_offset, icm_view mu,
+                                 int B, int C, int64_t P, icm_view y_hat_f32, icm_view y_hat_bf16_a,
+                                 icm_view y_hat_bf16_b, void *stream)
+{
+    ICM_CHECK_ARG(d_symbols, "icm_gc_dequantize: null argument");
+    GcArgs a{};
+    a.y = stream_view(const_cast<int32_t *>(d_symbols), stream_stride, stream_offset, P);
+    a.mu = as_view(mu);
+    a.yhat = as_view(y_hat_f32); a.bf_a = as_view(y_hat_bf16_a); a.bf_b = as_view(y_hat_bf16_b);
+    a.C = C; a.P = P;
+    return launch_gc<GC_DEQUANT>(a, B, stream);
+}
+
+extern "C" int icm_gc_likelihood(icm_view y, icm_view mu, icm_view scale, int B, int C, int64_t P, float scale_bound,
+                                 float likelihood_bound, icm_view y_hat_f32, icm_view likelihood, icm_view y_hat_bf16_a,
+                                 icm_view y_hat_bf16_b, void *stream)
+{
+    ICM_CHECK_ARG(y.ptr && mu.ptr && scale.ptr && likelihood.ptr, "icm_gc_likelihood: null argument");
+    GcArgs a{};
+    a.y = as_view(y); a.mu = as_view(mu); a.scale = as_view(scale);
+    a.yhat = as_view(y_hat_f32); a.lik = as_view(likelihood); a.bf_a = as_view(y_hat_bf16_a); a.bf_b = as_view(y_hat_bf16_b);
+    a.scale_bound = scale_bound; a.lik_bound = likelihood_bound; a.C = C; a.P = P;
+    return launch_gc<GC_LIK>(a, B, stream);
+}
+
+extern "C" int icm_add_lrp(icm_view y_hat_f32, icm_view lrp, int B, int C, int64_t P, icm_view y_hat_bf16_a,
+                           icm_view y_hat_bf16_b, void *stream)
+{
+    ICM_CHECK_ARG(y_hat_f32.ptr && lrp.ptr, "icm_add_lrp: null argument");
+    GcArgs a{};
+    a.y = as_view(lrp);
+    a.yhat = as_view(y_hat_f32); a.bf_a = as_view(y_hat_bf16_a); a.bf_b = as_view(y_hat_bf16_b);
+    a.C = C; a.P = P;
+    return launch_gc<GC_ADD>(a, B, stream);
+}
+
+extern "C" int icm_eb_process(int mode, icm_view z, int B, int C, int64_t P, const float *d_params,
+                              float likelihood_bound, int32_t *d_symbols, int32_t *d_indexes, icm_view z_hat_f32,
+                              icm_view z_hat_bf16, icm_view likelihood, void *stream)
+{
+    ICM_CHECK_ARG(mode >= 0 && mode <= 2 && d_params, "icm_eb_process: bad mode or null parameters");
+    ICM_CHECK_ARG(B > 0 && C > 0 && P > 0 && B <= 65535, "icm_eb_process: empty tensor");
+    ICM_CHECK_ARG(mode == 2 || z.ptr, "icm_eb_process: null z");
+    ICM_CHECK_ARG(mode == 1 || d_symbols, "icm_eb_process: null symbols");
+    ICM_CHECK_ARG(mode != 1 || likelihood.ptr, "icm_eb_process: null likelihood");
+    EbArgs a{};
+    a.z = as_view(z);
+    a.sym = stream_view(d_symbols, (long long)C * P, 0, P);
+    a.idx = stream_view(d_indexes, (long long)C * P, 0, P);
+    a.zhat = as_view(z_hat_f32); a.zhat_bf = as_view(z_hat_bf16); a.lik = as_view(likelihood);
+    a.params = d_params; a.lik_bound = likelihood_bound; a.C = C; a.P = P;
+    dim3 grid((unsigned)((P + TILE - 1) / TILE), (C + TILE - 1) / TILE, B);
+    cudaStream_t st = as_stream(stream);
+    if (mode == 0) eb_kernel<0><<<grid, THREADS, 0, st>>>(a);
+    else if (mode == 1) eb_kernel<1><<<grid, THREADS, 0, st>>>(a);
+    else eb_kernel<2><<<grid, THREADS, 0, st>>>(a);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}

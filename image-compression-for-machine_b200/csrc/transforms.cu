@@ -1,0 +1,381 @@
+// Memory-bound pieces of the STF transforms (rows T1, T2, T4, T6, T10 of SURVEY.md §8a): LayerNorm (with the
+// PatchMerging gather folded in), shifted-window attention, PatchEmbed and the 48->3 output convolution.
+// The GEMM-shaped work (qkv / proj / MLP / merge / split linears and all 3x3 / 5x5 convolutions) is in
+// conv.cu on the tensor cores; these kernels keep its operands in channels-last bf16 so that no
+// permute/contiguous/roll/window_partition copy of the reference (stf.py:42-53,97,167-191) exists at all.
+#include "common.cuh"
+
+namespace icm {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C (eps 1e-5), one warp per output row.  gather: row (b,h2,w2) is the concatenation of the
+// four tokens (2h2+dh, 2w2+dw) in the order (0,0),(1,0),(0,1),(1,1)  (stf.py:225-229), zero beyond H/W.
+template <typename OutT, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
+                                                        const float *__restrict__ beta, OutT *__restrict__ out,
+                                                        long long rows, int C, int gather, int H, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[MAXV]; // MAXV * 32 >= C
+
+    const int Cs = gather ? C / 4 : C; // channels per source token
+    int H2 = 0, W2 = 0, b = 0, h2 = 0, w2 = 0;
+    if (gather) {
+        H2 = (H + 1) / 2; W2 = (W + 1) / 2;
+        long long t = row;
+        w2 = (int)(t % W2); t /= W2;
+        h2 = (int)(t % H2); b = (int)(t / H2);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        float x = 0.f;
+        if (c < C) {
+            if (gather) {
+                const int k = c / Cs, cc = c - k * Cs;
+                const int hh = 2 * h2 + (k & 1), ww = 2 * w2 + (k >> 1);
+                if (hh < H && ww < W) x = in[(((long long)b * H + hh) * W + ww) * Cs + cc];
+            } else {
+                x = in[row * C + c];
+            }
+        }
+        v[i] = x;
+        sum += x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        const float d = (c < C) ? v[i] - mean : 0.f;
+        sq += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) {
+            const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            if constexpr (sizeof(OutT) == 2) out[row * C + c] = __float2bfloat16_rn(y);
+            else out[row * C + c] = y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float *__restrict__ in, long long rows, int C, long long in_pitch,
+                                                        __nv_bfloat16 *__restrict__ out, long long out_pitch)
+{
+    const long long total = rows * (C / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (C / 4);
+        const int c = (int)(i - r * (C / 4)) * 4;
+        const float4 f = *reinterpret_cast<const float4 *>(in + r * in_pitch + c);
+        const __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b2 = __floats2bfloat162_rn(f.z, f.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t *>(&a);
+        u.y = *reinterpret_cast<const uint32_t *>(&b2);
+        *reinterpret_cast<uint2 *>(out + r * out_pitch + c) = u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window attention, window 4x4 (16 tokens), head_dim 16 (every STF stage: 48/3 = 96/6 = 192/12 = 384/24).
+// One warp = one window x two heads: lane = head_sub * 16 + token.  K and V rows go through shared memory;
+// every lane owns one query row and produces one 16-wide output row.  The cyclic shift, the window
+// partition/reverse and the SW-MSA region mask are index arithmetic (stf.py:42-53,166-191,316-334).
+constexpr int WIN = 4, NTOK = 16, HD = 16;
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float *f)
+{
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out,
+                                                               const float *__restrict__ bias_table, int B, int H, int W, int C,
+                                                               int heads, int shift)
+{
+    extern __shared__ float s_bias[]; // [49][heads]
+    __shared__ float s_k[4][2][NTOK][HD + 1], s_v[4][2][NTOK][HD + 1];
+    for (int i = threadIdx.x; i < 49 * heads; i += blockDim.x) s_bias[i] = bias_table[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pairs = (heads + 1) / 2;
+    const int nWw = W / WIN, nWh = H / WIN;
+    const long long jobs = (long long)B * nWh * nWw * pairs;
+    const long long job = (long long)blockIdx.x * 4 + warp;
+    if (job >= jobs) return;
+    const int pair = (int)(job % pairs);
+    long long t = job / pairs;
+    const int ww = (int)(t % nWw); t /= nWw;
+    const int wh = (int)(t % nWh);
+    const int b = (int)(t / nWh);
+    const int hs_sub = lane >> 4, tok = lane & 15;
+    const int head = pair * 2 + hs_sub;
+    const bool active = head < heads;
+    const int ih = tok >> 2, iw = tok & 3;
+    // position in the shifted grid and in the original grid
+    const int hs = wh * WIN + ih, ws = ww * WIN + iw;
+    int h = hs + shift, w = ws + shift;
+    if (h >= H) h -= H;
+    if (w >= W) w -= W;
+    const long long token = ((long long)b * H + h) * W + w;
+    int label = 0;
+    if (shift > 0) {
+        const int r = hs < H - WIN ? 0 : (hs < H - shift ? 1 : 2);
+        const int c = ws < W - WIN ? 0 : (ws < W - shift ? 1 : 2);
+        label = 3 * r + c;
+    }
+    float q[HD];
+    if (active) {
+        const __nv_bfloat16 *row = qkv + token * 3 * C + head * HD;
+        float tmp[HD];
+        unpack8(*reinterpret_cast<const uint4 *>(row), q);
+        unpack8(*reinterpret_cast<const uint4 *>(row + 8), q + 8);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] *= 0.25f; // head_dim ** -0.5
+        unpack8(*reinterpret_cast<const uint4 *>(row + C), tmp);
+        unpack8(*reinterpret_cast<const uint4 *>(row + C + 8), tmp + 8);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) s_k[warp][hs_sub][tok][d] = tmp[d];
+        unpack8(*reinterpret_cast<const uint4 *>(row + 2 * C), tmp);
+        unpack8(*reinterpret_cast<const uint4 *>(row + 2 * C + 8), tmp + 8);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) s_v[warp][hs_sub][tok][d] = tmp[d];
+    }
+    __syncwarp();
+    if (!active) return;
+    float sc[NTOK];
+    float mx = -1e30f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) a += q[d] * s_k[warp][hs_sub][j][d];
+        const int jh = j >> 2, jw = j & 3;
+        a += s_bias[((ih - jh + WIN - 1) * (2 * WIN - 1) + (iw - jw + WIN - 1)) * heads + head];
+        if (shift > 0) {
+            const int hj = wh * WIN + jh, wj = ww * WIN + jw;
+            const int lj = 3 * (hj < H - WIN ? 0 : (hj < H - shift ? 1 : 2)) + (wj < W - WIN ? 0 : (wj < W - shift ? 1 : 2));
+            if (lj != label) a += -100.0f;
+        }
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+    const float inv = 1.0f / den;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+        const float pj = sc[j] * inv;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] += pj * s_v[warp][hs_sub][j][d];
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * d], o[2 * d + 1]);
+        pk[d] = *reinterpret_cast<const uint32_t *>(&h2);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(out + token * C + head * HD);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PatchEmbed: Conv2d(3 -> C, k=2, s=2) + LayerNorm(C); C <= 64.  One thread per output token.
+__global__ void __launch_bounds__(128) patch_embed_kernel(const float *__restrict__ img, const float *__restrict__ w,
+                                                          const float *__restrict__ bias, const float *__restrict__ gamma,
+                                                          const float *__restrict__ beta, float *__restrict__ tokens,
+                                                          int B, int H, int W, int C)
+{
+    __shared__ float s_w[64 * 12], s_b[64], s_g[64], s_be[64];
+    for (int i = threadIdx.x; i < C * 12; i += blockDim.x) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_b[i] = bias[i]; s_g[i] = gamma[i]; s_be[i] = beta[i]; }
+    __syncthreads();
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const long long total = (long long)B * H2 * W2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int w2 = (int)(idx % W2);
+    const int h2 = (int)((idx / W2) % H2);
+    const int b = (int)(idx / ((long long)W2 * H2));
+    float x[12]; // [ci][kh][kw], zero padded on the bottom/right (stf.py:368-372)
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 2; ++kw) {
+                const int hh = 2 * h2 + kh, ww = 2 * w2 + kw;
+                x[ci * 4 + kh * 2 + kw] = (hh < H && ww < W) ? img[(((long long)b * 3 + ci) * H + hh) * W + ww] : 0.f;
+            }
+    float y[64];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        float a = 0.f;
+        if (c < C) {
+            a = s_b[c];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) a += s_w[c * 12 + k] * x[k];
+            sum += a;
+        }
+        y[c] = a;
+    }
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) if (c < C) { const float d = y[c] - mean; sq += d * d; }
+    const float rstd = rsqrtf(sq / (float)C + 1e-5f);
+    float *dst = tokens + idx * C;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) if (c < C) dst[c] = (y[c] - mean) * rstd * s_g[c] + s_be[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output convolution C -> 3, 3x3, pad 1, bf16 channels-last in, fp32 NCHW image out (stf.py:466,784).
+// 16x16 pixel tile per CTA with an 18x18 halo tile in shared memory.
+constexpr int FT = 16;
+
+__global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16 *__restrict__ in, const float *__restrict__ w,
+                                                         const float *__restrict__ bias, float *__restrict__ img, int B, int H,
+                                                         int W, int C, int clamp01)
+{
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int CP = C / 2 + 1; // 32-bit words per pixel (+1 pad: odd stride, conflict-free)
+    uint32_t *s_in = reinterpret_cast<uint32_t *>(fsm);                       // [(FT+2)^2][CP]
+    float *s_w = reinterpret_cast<float *>(s_in + (FT + 2) * (FT + 2) * CP);   // [3][9][C]
+    const int b = blockIdx.z, h0 = blockIdx.y * FT, w0 = blockIdx.x * FT;
+    for (int i = threadIdx.x; i < 3 * 9 * C; i += blockDim.x) {
+        // torch layout [co][ci][kh][kw] -> [co][tap][ci]
+        const int ci = i % C, tap = (i / C) % 9, co = i / (9 * C);
+        s_w[i] = w[(co * C + ci) * 9 + tap];
+    }
+    const int words = C / 2;
+    for (int i = threadIdx.x; i < (FT + 2) * (FT + 2) * words; i += blockDim.x) {
+        const int cw = i % words, pix = i / words;
+        const int hh = h0 + pix / (FT + 2) - 1, ww = w0 + pix % (FT + 2) - 1;
+        uint32_t v = 0;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            v = reinterpret_cast<const uint32_t *>(in + (((long long)b * H + hh) * W + ww) * C)[cw];
+        s_in[pix * CP + cw] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x % FT, ty = threadIdx.x / FT;
+    const int oh = h0 + ty, ow = w0 + tx;
+    float acc0 = bias[0], acc1 = bias[1], acc2 = bias[2];
+    for (int tap = 0; tap < 9; ++tap) {
+        const int pix = (ty + tap / 3) * (FT + 2) + tx + tap % 3;
+        const uint32_t *src = s_in + pix * CP;
+        const float *w0p = s_w + (0 * 9 + tap) * C, *w1p = s_w + (1 * 9 + tap) * C, *w2p = s_w + (2 * 9 + tap) * C;
+        for (int cw = 0; cw < words; ++cw) {
+            const uint32_t u = src[cw];
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+            acc0 += f.x * w0p[2 * cw] + f.y * w0p[2 * cw + 1];
+            acc1 += f.x * w1p[2 * cw] + f.y * w1p[2 * cw + 1];
+            acc2 += f.x * w2p[2 * cw] + f.y * w2p[2 * cw + 1];
+        }
+    }
+    if (oh < H && ow < W) {
+        if (clamp01) { acc0 = fminf(fmaxf(acc0, 0.f), 1.f); acc1 = fminf(fmaxf(acc1, 0.f), 1.f); acc2 = fminf(fmaxf(acc2, 0.f), 1.f); }
+        const long long plane = (long long)H * W;
+        float *dst = img + (long long)b * 3 * plane + (long long)oh * W + ow;
+        dst[0] = acc0; dst[plane] = acc1; dst[2 * plane] = acc2;
+    }
+}
+
+}  // namespace icm
+
+using namespace icm;
+
+extern "C" int icm_layernorm(const float *d_in, const float *d_gamma, const float *d_beta, void *d_out, int out_dtype,
+                             int64_t rows, int C, int gather, int B, int H, int W, void *stream)
+{
+    ICM_CHECK_ARG(d_in && d_gamma && d_beta && d_out, "icm_layernorm: null argument");
+    ICM_CHECK_ARG(C > 0 && C <= 768, "icm_layernorm: C=%d outside (0,768]", C);
+    ICM_CHECK_ARG(!gather || (C % 4 == 0 && rows == (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2)), "icm_layernorm: gather shape mismatch");
+    ICM_CHECK_ARG(rows > 0, "icm_layernorm: no rows");
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = as_stream(stream);
+#define ICM_LN_LAUNCH(V)                                                                                                   \
+    do {                                                                                                                   \
+        if (out_dtype == ICM_OUT_BF16)                                                                                     \
+            layernorm_kernel<__nv_bfloat16, V><<<grid, 256, 0, st>>>(d_in, d_gamma, d_beta, (__nv_bfloat16 *)d_out, rows, C, gather, H, W); \
+        else                                                                                                               \
+            layernorm_kernel<float, V><<<grid, 256, 0, st>>>(d_in, d_gamma, d_beta, (float *)d_out, rows, C, gather, H, W);  \
+    } while (0)
+    if (C <= 64) ICM_LN_LAUNCH(2);
+    else if (C <= 128) ICM_LN_LAUNCH(4);
+    else if (C <= 256) ICM_LN_LAUNCH(8);
+    else if (C <= 384) ICM_LN_LAUNCH(12);
+    else ICM_LN_LAUNCH(24);
+#undef ICM_LN_LAUNCH
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_cast_bf16(const float *d_in, int64_t rows, int C, int64_t in_pitch, void *d_out, int64_t out_pitch, void *stream)
+{
+    ICM_CHECK_ARG(d_in && d_out && rows > 0 && C > 0 && C % 4 == 0 && in_pitch % 4 == 0 && out_pitch % 4 == 0, "icm_cast_bf16: bad arguments");
+    const long long total = rows * (C / 4);
+    const int grid = (int)min((total + 255) / 256, (long long)sm_count() * 16);
+    cast_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_in, rows, C, in_pitch, (__nv_bfloat16 *)d_out, out_pitch);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_window_attention(const void *d_qkv, void *d_out, const float *d_bias_table, int B, int H, int W,
+                                    int C, int heads, int window, int shift, void *stream)
+{
+    ICM_CHECK_ARG(d_qkv && d_out && d_bias_table, "icm_window_attention: null argument");
+    if (window != WIN || C != heads * HD) { set_error("icm_window_attention: only window 4 / head_dim 16 is built (got window %d, head_dim %d)", window, heads ? C / heads : 0); return ICM_ERR_UNSUPPORTED; }
+    if (H % WIN || W % WIN) { set_error("icm_window_attention: H=%d W=%d must be multiples of the window (pad the image to a multiple of 64 as the reference's eval does)", H, W); return ICM_ERR_UNSUPPORTED; }
+    ICM_CHECK_ARG(shift >= 0 && shift < WIN, "icm_window_attention: bad shift");
+    const long long jobs = (long long)B * (H / WIN) * (W / WIN) * ((heads + 1) / 2);
+    const unsigned grid = (unsigned)((jobs + 3) / 4);
+    window_attention_kernel<<<grid, 128, 49 * heads * sizeof(float), as_stream(stream)>>>(
+        (const __nv_bfloat16 *)d_qkv, (__nv_bfloat16 *)d_out, d_bias_table, B, H, W, C, heads, shift);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_patch_embed(const float *d_img, const float *d_w, const float *d_b, const float *d_gamma,
+                               const float *d_beta, float *d_tokens, int B, int H, int W, int C, void *stream)
+{
+    ICM_CHECK_ARG(d_img && d_w && d_b && d_gamma && d_beta && d_tokens, "icm_patch_embed: null argument");
+    ICM_CHECK_ARG(C > 0 && C <= 64 && B > 0 && H > 0 && W > 0, "icm_patch_embed: bad shape");
+    const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
+    patch_embed_kernel<<<(unsigned)((total + 127) / 128), 128, 0, as_stream(stream)>>>(d_img, d_w, d_b, d_gamma, d_beta, d_tokens, B, H, W, C);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_final_conv(const void *d_in_bf16, const float *d_w, const float *d_b, float *d_img, int B, int H,
+                              int W, int C, int clamp01, void *stream)
+{
+    ICM_CHECK_ARG(d_in_bf16 && d_w && d_b && d_img, "icm_final_conv: null argument");
+    ICM_CHECK_ARG(C > 0 && C % 2 == 0 && C <= 96, "icm_final_conv: C=%d unsupported", C);
+    const size_t smem = (size_t)(FT + 2) * (FT + 2) * (C / 2 + 1) * 4 + (size_t)27 * C * 4;
+    dim3 grid((W + FT - 1) / FT, (H + FT - 1) / FT, B);
+    static thread_local bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        ICM_CUDA(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    final_conv_kernel<<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16 *)d_in_bf16, d_w, d_b, d_img, B, H, W, C, clamp01);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}

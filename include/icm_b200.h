@@ -1,0 +1,202 @@
+/*
+ * icm_b200.h -- C ABI of the B200-native hot path of stm233/image-compression-for-machine.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a cudaStream_t (passed as void*); no torch,
+ * pybind11 or C++ types.  Each entry point names the reference interface it replaces (paths relative
+ * to the reference tree, "ans.so@0x...." = symbol offset inside the reference's shipped
+ * compressai/ans.cpython-38-x86_64-linux-gnu.so whose sources are absent).
+ *
+ * Conventions
+ *   - every function returns ICM_OK (0) or a negative ICM_ERR_* code and never throws;
+ *     icm_last_error() returns a thread-local message for the last failure;
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers;
+ *   - all device work is enqueued on `stream` and is asynchronous unless stated otherwise;
+ *   - "stream order" of an image's symbols = the order the reference feeds its coder:
+ *       y: slice-major, then (c, h, w) inside a slice   (compressai/models/stf.py:718-719)
+ *       z: (c, h, w)                                      (entropy_models.py:227-235)
+ */
+#ifndef ICM_B200_H
+#define ICM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICM_OK 0
+#define ICM_ERR_INVALID_ARG (-1)
+#define ICM_ERR_CUDA (-2)
+#define ICM_ERR_NO_DEVICE (-3)
+#define ICM_ERR_CAPACITY (-4)
+#define ICM_ERR_BAD_INDEX (-5)
+#define ICM_ERR_UNSUPPORTED (-6)
+
+const char *icm_last_error(void);
+/* ABI version of this library (bumped on incompatible changes). */
+int icm_abi_version(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches). */
+int64_t icm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * R5  compressai._CXX.pmf_to_quantized_cdf(list[float] pmf, int precision) -> list[int]
+ *     (_CXX.so@0x68c0; called from entropy_models.py:60-63).  HOST function, no GPU needed.
+ *     out must hold n+1 entries.  Returns n+1 on success. */
+int icm_pmf_to_quantized_cdf(const float *h_pmf, int n, int precision, uint32_t *h_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantised-CDF tables resident on the device.  Replaces the (cdfs, cdfs_sizes, offsets) list
+ * arguments that every compressai.ans call receives and that pybind11 re-copies per call
+ * (entropy_models.py:231-233, stf.py:694-696,727,766). h_cdfs is row-major int32 [n_cdf][stride]. */
+typedef struct icm_tables icm_tables;
+int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, const int32_t *h_sizes,
+                      const int32_t *h_offsets, icm_tables **out);
+void icm_tables_destroy(icm_tables *t);
+
+/* ------------------------------------------------------------------------------------------------
+ * R1+R2+R3  ans.RansEncoder.encode_with_indexes / BufferedRansEncoder.encode_with_indexes + flush
+ *     (ans.so@0x8d70, @0x8a10, @0x8730; third_party/ryg_rans/rans64.h:65-103).
+ *     Encodes n_streams independent streams (one 64-bit rANS state each, exactly the reference's
+ *     coder).  Stream s covers d_symbols/d_indexes[s*n_per_stream .. +n_per_stream) (stream order).
+ *     d_work:   scratch, icm_rans_encode_workspace_bytes(n_streams, n_per_stream) bytes.
+ *     d_packed: output, the streams' bytes back to back; capacity `packed_capacity` bytes.
+ *     d_sizes:  int32[n_streams+1]: byte length of every stream, then the total; a stream whose
+ *               symbols referenced an invalid table index reports ICM_ERR_BAD_INDEX there. */
+int64_t icm_rans_encode_workspace_bytes(int n_streams, int64_t n_per_stream);
+int icm_rans_encode_batch(const icm_tables *t, const int32_t *d_symbols, const int32_t *d_indexes,
+                          int n_streams, int64_t n_per_stream, void *d_work, uint8_t *d_packed,
+                          int64_t packed_capacity, int32_t *d_sizes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * R4  ans.RansDecoder.set_stream / decode_stream / decode_with_indexes
+ *     (ans.so@0x7c40, @0x7ce0, @0x8060; rans64.h:107-142).
+ *     A decoder object holds n_streams {state, read position} pairs on the device, which persist
+ *     across decode_step calls like the reference object does across decode_stream calls
+ *     (stf.py:751-766: one set_stream, twelve decode_stream calls per image). */
+typedef struct icm_rans_decoder icm_rans_decoder;
+int icm_rans_decoder_create(int n_streams, icm_rans_decoder **out);
+void icm_rans_decoder_destroy(icm_rans_decoder *d);
+/* d_bytes: all streams back to back (each length a multiple of 4, 4-byte aligned start);
+ * h_offsets/h_sizes: byte offset and length of every stream inside d_bytes. */
+int icm_rans_decoder_set_streams(icm_rans_decoder *d, const uint8_t *d_bytes, const int64_t *h_offsets,
+                                 const int64_t *h_sizes, void *stream);
+/* Decodes the next n_per_stream symbols of every stream.  d_indexes / d_out: [n_streams][n_per_stream]. */
+int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, const int32_t *d_indexes,
+                          int64_t n_per_stream, int32_t *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Strided view of a [B, C, P] tensor (P = H*W pixels).  NCHW: sb=C*P, sc=P, sp=1;
+ * NHWC with row pitch `pitch`: sb=P*pitch, sc=1, sp=pitch.  Strides are in elements. */
+typedef struct {
+    void *ptr;
+    int64_t sb, sc, sp;
+} icm_view;
+
+/* E1+E3 (+E2)  GaussianConditional.build_indexes + quantize(..., "symbols", means) and ŷ = q + means
+ *     (entropy_models.py:661-666, :126-150; stf.py:714-716).  fp32 in; int32 symbols / indexes written
+ *     in stream order at d_symbols[b*stream_stride + stream_offset + c*P + p].  Optional outputs
+ *     (ptr may be NULL): y_hat fp32 view and up to two bf16 views (the conv stacks' support buffers).
+ *     mu may be absent (means=None); scale and d_indexes may both be absent (plain quantize). */
+int icm_gc_quantize_index(icm_view y, icm_view mu, icm_view scale, int B, int C, int64_t P,
+                          const float *d_scale_table, int n_levels, float scale_bound,
+                          int32_t *d_symbols, int32_t *d_indexes, int64_t stream_stride, int64_t stream_offset,
+                          icm_view y_hat_f32, icm_view y_hat_bf16_a, icm_view y_hat_bf16_b, void *stream);
+
+/* E3 alone, for the decoder: indexes in stream order from a scale view (stf.py:764). */
+int icm_gc_build_indexes(icm_view scale, int B, int C, int64_t P, const float *d_scale_table, int n_levels,
+                         float scale_bound, int32_t *d_indexes, int64_t stream_stride, int64_t stream_offset,
+                         void *stream);
+
+/* E2  EntropyModel.dequantize(symbols, means) (entropy_models.py:159-165; stf.py:767-768): symbols in
+ *     stream order -> ŷ = float(q) + mu, same optional outputs as above. */
+int icm_gc_dequantize(const int32_t *d_symbols, int64_t stream_stride, int64_t stream_offset, icm_view mu,
+                      int B, int C, int64_t P, icm_view y_hat_f32, icm_view y_hat_bf16_a,
+                      icm_view y_hat_bf16_b, void *stream);
+
+/* E4  GaussianConditional.forward in eval mode (entropy_models.py:626-659): ŷ = round(y-mu)+mu and
+ *     likelihood = max(Phi((.5-|ŷ-mu|)/s) - Phi((-.5-|ŷ-mu|)/s), bound), s = max(scale, scale_bound). */
+int icm_gc_likelihood(icm_view y, icm_view mu, icm_view scale, int B, int C, int64_t P, float scale_bound,
+                      float likelihood_bound, icm_view y_hat_f32, icm_view likelihood, icm_view y_hat_bf16_a,
+                      icm_view y_hat_bf16_b, void *stream);
+
+/* y_hat += lrp (fp32), refreshing the bf16 copies (stf.py:628-631, 723-726, 773-776). */
+int icm_add_lrp(icm_view y_hat_f32, icm_view lrp, int B, int C, int64_t P, icm_view y_hat_bf16_a,
+                icm_view y_hat_bf16_b, void *stream);
+
+/* E5/E6  EntropyBottleneck (entropy_models.py:400-433, 446-489, 492-522).
+ *     d_params: the module's parameters packed per channel, 59 floats each:
+ *       softplus-free raw _matrix0[3] _bias0[3] _factor0[3] _matrix1[9] _bias1[3] _factor1[3]
+ *       _matrix2[9] _bias2[3] _factor2[3] _matrix3[9] _bias3[3] _factor3[3] _matrix4[3] _bias4[1]
+ *       median[1]   (filters (3,3,3,3) only, the reference's default and the only one its models use).
+ *     mode 0: symbols = round(z - median) in stream order (c,h,w) + ẑ          (compress, :508-515)
+ *     mode 1: ẑ and likelihood (eval forward, :446-489)
+ *     mode 2: ẑ = float(symbols) + median                                       (decompress, :517-522) */
+#define ICM_EB_PARAMS_PER_CHANNEL 59
+int icm_eb_process(int mode, icm_view z, int B, int C, int64_t P, const float *d_params,
+                   float likelihood_bound, int32_t *d_symbols, int32_t *d_indexes, icm_view z_hat_f32,
+                   icm_view z_hat_bf16, icm_view likelihood, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Transforms (rows T1-T11).  Activations are channels-last; GEMM operands bf16, accumulation fp32.
+ *
+ * icm_conv2d: implicit-GEMM convolution / linear layer on the tcgen05 tensor cores.
+ *     in:   bf16 NHWC [B, H, W, in_pitch], the first Cin channels are read;
+ *     w:    bf16 [Cout_pad][KH*KW*Cin_pad] (tap-major, then channel; Cin_pad = Cin rounded up to 64 with
+ *           zero weights), packed by icm_pack_conv_weight;
+ *     out:  row pitch out_pitch, channel offset applied by the caller through the pointer.
+ *     Replaces torch.conv2d / F.linear at stf.py:34-40,97,119,233,256,464-546 and cnn.py:31-52. */
+#define ICM_ACT_NONE 0
+#define ICM_ACT_GELU 1       /* exact erf form (nn.GELU default) */
+#define ICM_ACT_HALF_TANH 2  /* 0.5*tanh(x)  (stf.py:628) */
+#define ICM_ACT_SIGMOID 3
+#define ICM_OUT_BF16 0
+#define ICM_OUT_F32 1
+typedef struct {
+    const void *in;        /* bf16 */
+    const void *weight;    /* bf16 packed */
+    const float *bias;     /* fp32 [Cout] or NULL */
+    void *out;
+    const float *residual; /* fp32, added after activation (same indexing as out), or NULL */
+    int B, H, W;           /* input spatial size */
+    int Cin, in_pitch;     /* channels read per pixel (any value; zero-filled up to a multiple of 64) and row pitch */
+    int Cout, out_pitch;
+    int KH, KW, stride, pad;
+    int act, out_dtype;
+    int pixel_shuffle;     /* 0 or r: output written as PixelShuffle(r) of the conv result */
+    int res_pitch;
+} icm_conv_args;
+int icm_conv2d(const icm_conv_args *a, void *stream);
+int icm_pack_conv_weight(const float *d_w_oihw, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,
+                         int pixel_shuffle, void *d_out_bf16, void *stream);
+
+/* LayerNorm over the last dim (eps 1e-5), fp32 in -> bf16 or fp32 out.  gather = 1 applies the
+ * PatchMerging 2x2 gather first (stf.py:225-232: channel blocks x(0,0),x(1,0),x(0,1),x(1,1)). */
+int icm_layernorm(const float *d_in, const float *d_gamma, const float *d_beta, void *d_out, int out_dtype,
+                  int64_t rows, int C, int gather, int B, int H, int W, void *stream);
+
+/* fp32 -> bf16 copy of a [rows, C] block with row pitches (elements); C % 4 == 0. */
+int icm_cast_bf16(const float *d_in, int64_t rows, int C, int64_t in_pitch, void *d_out, int64_t out_pitch, void *stream);
+
+/* Per-stream status of a decoder (0 or ICM_ERR_BAD_INDEX); synchronises the stream. */
+int icm_rans_decoder_status(icm_rans_decoder *d, int32_t *h_status, void *stream);
+
+/* T4 core: softmax(q k^T * scale + bias[rel_idx] + mask) v per (window, head) on a qkv tensor
+ *     bf16 [B, H, W, 3C] (feature order s*C + h*hd + d, stf.py:97), writing bf16 [B, H, W, C] in token
+ *     order; `shift` > 0 applies the cyclic shift and the region mask (stf.py:166-171,316-334). */
+int icm_window_attention(const void *d_qkv, void *d_out, const float *d_bias_table, int B, int H, int W,
+                         int C, int heads, int window, int shift, void *stream);
+
+/* T1  PatchEmbed: Conv2d(3->C, k2, s2) + LayerNorm(C) from an NCHW fp32 image to fp32 tokens
+ *     (stf.py:365-381). */
+int icm_patch_embed(const float *d_img, const float *d_w, const float *d_b, const float *d_gamma,
+                    const float *d_beta, float *d_tokens, int B, int H, int W, int C, void *stream);
+
+/* T10 tail: Conv2d(C->3, k3, p1) from bf16 NHWC to an fp32 NCHW image, optional clamp to [0,1]
+ *     (stf.py:466,784). */
+int icm_final_conv(const void *d_in_bf16, const float *d_w, const float *d_b, float *d_img, int B, int H,
+                   int W, int C, int clamp01, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICM_B200_H */

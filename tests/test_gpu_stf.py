@@ -1,0 +1,143 @@
+"""End-to-end STF (compressai.models.SymmetricalTransFormer on the CUDA kernels) vs fixtures recorded from
+the reference model run on the CPU in fp32 (oracle/make_golden.py) and vs the pinned functional oracle.
+
+Tolerances (north_star): x_hat within 0.01 dB PSNR; bit-exact strings where inputs are identical
+(self-consistency, batch invariance); likelihoods are checked at 1e-3 on identical inputs in
+test_gpu_entropy.py, here only the total rate is compared (the transforms run with bf16 operands)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+PSNR_TOL_DB = 0.01
+
+
+def psnr(a, b):
+    return float(-10 * torch.log10(torch.mean((a.float().cpu() - b.float().cpu()) ** 2)))
+
+
+@pytest.fixture(scope="module")
+def model():
+    from compressai.zoo import models
+    from oracle import stf_ref, weights
+
+    m = models["stf"]()
+    sd = weights.seeded_state_dict(stf_ref.template_state_dict(), seed=0, stress=True)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    m.update(force=True)
+    return m.cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "stf_small.npz"))
+
+
+@pytest.fixture(scope="module")
+def x():
+    from oracle import weights
+
+    return weights.seeded_image((1, 3, 128, 192), seed=0)
+
+
+def test_tables_match_reference_update(model, gold):
+    eb = model.entropy_bottleneck
+    assert np.array_equal(eb.quantized_cdf.cpu().numpy(), gold["eb_cdf"])
+    assert np.array_equal(eb.cdf_length.cpu().numpy(), gold["eb_len"]) and np.array_equal(eb.offset.cpu().numpy(), gold["eb_off"])
+
+
+def test_analysis_and_hyper_transforms_close_to_reference(model, gold, x):
+    B = 1
+    y, h, w = model._analysis(x.cuda())
+    assert (h, w) == (8, 12)
+    y_ref = torch.from_numpy(gold["y"]).permute(0, 2, 3, 1).reshape(-1, 384)
+    rel = float((y.cpu() - y_ref).norm() / y_ref.norm())
+    assert rel < 2e-2, rel
+    z, zh, zw = model._hyper_analysis(y, B, h, w)
+    z_ref = torch.from_numpy(gold["z"]).permute(0, 2, 3, 1).reshape(-1, 192)
+    rel = float((z.cpu() - z_ref).norm() / z_ref.norm())
+    assert (zh, zw) == (2, 3) and rel < 3e-2, rel
+
+
+def test_forward_matches_reference_quality_and_rate(model, gold, x):
+    out = model(x.cuda())
+    assert out["x_hat"].shape == (1, 3, 128, 192) and out["likelihoods"]["y"].shape == (1, 384, 8, 12)
+    assert out["likelihoods"]["z"].shape == (1, 192, 2, 3)
+    x_ref = torch.from_numpy(gold["x_hat"])
+    assert abs(psnr(x, out["x_hat"]) - psnr(x, x_ref)) < PSNR_TOL_DB, (psnr(x, out["x_hat"]), psnr(x, x_ref))
+    bits = lambda l: float(-torch.log2(torch.as_tensor(l).float().cpu()).sum())
+    by, by_ref = bits(out["likelihoods"]["y"]), bits(gold["y_lik"])
+    bz, bz_ref = bits(out["likelihoods"]["z"]), bits(gold["z_lik"])
+    assert abs(by - by_ref) / by_ref < 2e-2, (by, by_ref)
+    assert abs(bz - bz_ref) / bz_ref < 2e-2, (bz, bz_ref)
+
+
+def test_compress_decompress_self_consistency(model, gold, x):
+    """The identity the reference's eval relies on: decompress(compress(x)) == clamp(forward(x).x_hat), exactly."""
+    xc = x.cuda()
+    c = model.compress(xc)
+    assert list(c["shape"]) == [2, 3] and len(c["strings"]) == 2 and len(c["strings"][0]) == 1 and len(c["strings"][1]) == 1
+    d = model.decompress(c["strings"], c["shape"])
+    f = model(xc)
+    assert torch.equal(d["x_hat"], f["x_hat"].clamp(0, 1))
+    # stream sizes are in the reference's ballpark (same weights, same image; bf16 transforms)
+    ny, nz = len(c["strings"][0][0]), len(c["strings"][1][0])
+    assert abs(ny - gold["y_string"].size) / gold["y_string"].size < 3e-2, (ny, gold["y_string"].size)
+    assert abs(nz - gold["z_string"].size) / gold["z_string"].size < 5e-2, (nz, gold["z_string"].size)
+    assert abs(psnr(x, d["x_hat"]) - psnr(x, torch.from_numpy(gold["x_hat"]).clamp(0, 1))) < PSNR_TOL_DB
+
+
+def test_batch_strings_equal_single_image_strings(model):
+    """Config 3 semantics: per-image strings of a batch == the B=1 strings of each image (bit-exact), and the
+    batch decodes back to the per-image reconstructions."""
+    from oracle import weights
+
+    xs = torch.cat([weights.seeded_image((1, 3, 128, 128), seed=s) for s in (1, 2, 3)]).cuda()
+    cb = model.compress(xs)
+    assert len(cb["strings"][0]) == 3 and len(cb["strings"][1]) == 3
+    db = model.decompress(cb["strings"], cb["shape"])
+    for b in range(3):
+        c1 = model.compress(xs[b:b + 1])
+        assert c1["strings"][0][0] == cb["strings"][0][b]
+        assert c1["strings"][1][0] == cb["strings"][1][b]
+        d1 = model.decompress(c1["strings"], c1["shape"])
+        assert torch.equal(d1["x_hat"][0], db["x_hat"][b])
+
+
+def test_strings_decode_with_the_cpu_oracle(model, x):
+    """Cross-implementation check: the GPU-produced y-string of an image decodes, with the pinned CPU coder
+    and the GPU-side indexes, to the symbols the GPU encoder consumed."""
+    from oracle import coder, entropy
+
+    xc = x.cuda()
+    B = 1
+    y, h, w = model._analysis(xc)
+    z, zh, zw = model._hyper_analysis(y, B, h, w)
+    c = model.compress(xc)
+    # recompute symbols/indexes exactly as compress does
+    from compressai._native import NULL_VIEW, check, lib, stream_ptr, view_bcp
+
+    eb = model.entropy_bottleneck
+    Pz = zh * zw
+    z_sym = torch.empty((B, 192 * Pz), dtype=torch.int32, device="cuda")
+    z_idx = torch.empty_like(z_sym)
+    z_hat = torch.empty((B * Pz, 192), dtype=torch.bfloat16, device="cuda")
+    check(lib().icm_eb_process(0, view_bcp(z, B, 192, Pz), B, 192, Pz, eb.packed_params().data_ptr(), 0.0, z_sym.data_ptr(),
+                               z_idx.data_ptr(), NULL_VIEW, view_bcp(z_hat, B, 192, Pz), NULL_VIEW, stream_ptr()))
+    ms, ss = model._hyper_synthesis(z_hat, B, zh, zw)
+    _, sym, idx = model._slice_loop("compress", B, h, w, ms, ss, y=y)
+    cdf, lengths, offsets = entropy.gc_tables()
+    got = coder.RansDecoder().decode_with_indexes(c["strings"][0][0], idx[0].cpu().numpy(), cdf, lengths, offsets)
+    assert np.array_equal(got, sym[0].cpu().numpy())
+    assert coder.rans_encode(sym[0].cpu().numpy(), idx[0].cpu().numpy(), cdf, lengths, offsets) == c["strings"][0][0]
+    assert int(idx.unique().numel()) > 20  # the stress weights exercise many CDF tables
+
+
+def test_input_validation(model):
+    with pytest.raises(ValueError):
+        model.compress(torch.zeros(1, 3, 100, 128, device="cuda"))
+    with pytest.raises(ValueError):
+        model.decompress([[b"\0" * 8], [b"\0" * 8, b"\0" * 8]], (2, 2))
