@@ -80,8 +80,9 @@ class Tables:
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h and _native._lib is not None:
-            _native._lib.icm_tables_destroy(h)
+        L = getattr(_native, "_lib", None) if _native is not None else None  # module globals vanish at interpreter exit
+        if h and L is not None:
+            L.icm_tables_destroy(h)
             self.handle = None
 
 
@@ -167,8 +168,9 @@ class StreamDecoder:
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h and _native._lib is not None:
-            _native._lib.icm_rans_decoder_destroy(h)
+        L = getattr(_native, "_lib", None) if _native is not None else None
+        if h and L is not None:
+            L.icm_rans_decoder_destroy(h)
             self.handle = None
 
     def set_streams(self, strings):

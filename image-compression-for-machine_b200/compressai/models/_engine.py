@@ -28,7 +28,12 @@ class PackedConv:
         self.w = torch.empty((cout_pad, self.KH * self.KW * cin_pad), dtype=torch.bfloat16, device=w.device)
         check(lib().icm_pack_conv_weight(w.data_ptr(), self.Cout, self.Cin, self.KH, self.KW, cin_pad, cout_pad, self.ps,
                                          self.w.data_ptr(), stream_ptr()), "icm_pack_conv_weight")
-        self.bias = None if bias is None else bias.detach().float().contiguous().clone()
+        self.bias = None
+        if bias is not None:
+            b = bias.detach().float()
+            if self.ps:  # GEMM column (i*r+j)*Cq + c holds conv channel c*r^2 + (i*r+j): permute the bias alike
+                b = b.reshape(self.Cout // (self.ps * self.ps), self.ps * self.ps).t()
+            self.bias = b.contiguous().reshape(-1).clone()
 
 
 class Engine:
@@ -42,7 +47,8 @@ class Engine:
     # ---------------------------------------------------------------------------------- weights
     def packed(self, module, ps=0):
         key = (id(module), ps)
-        pk = self._packed.get(key)
+        hit = self._packed.get(key)
+        pk = hit[0] if hit is not None else None
         if pk is None:
             if isinstance(module, torch.nn.Conv2d):
                 pk = PackedConv(module.weight, module.bias, module.stride[0], module.padding[0], ps)
@@ -50,16 +56,16 @@ class Engine:
                 pk = PackedConv(module.weight, module.bias, 1, 0, ps)
             else:
                 raise TypeError(type(module))
-            self._packed[key] = pk
+            self._packed[key] = (pk, module)  # holding the module keeps its id() from being reused
         return pk
 
     def f32(self, p):
         key = (id(p), "f32")
-        t = self._packed.get(key)
-        if t is None:
-            t = p.detach().float().contiguous()
-            self._packed[key] = t
-        return t
+        hit = self._packed.get(key)
+        if hit is None:
+            hit = (p.detach().float().contiguous(), p)
+            self._packed[key] = hit
+        return hit[0]
 
     # ---------------------------------------------------------------------------------- kernels
     def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None):

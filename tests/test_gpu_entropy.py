@@ -61,7 +61,8 @@ def test_layouts_agree(gc):
     yh = torch.zeros(B * P, 64, device="cuda")
     bf = torch.zeros(B * P, 48, dtype=torch.bfloat16, device="cuda")
     tab = gc.scale_table_device(y.device)
-    check(lib().icm_gc_quantize_index(view_bcp(wide, B, C, P, 40), view_bcp(cl(mu), B, C, P), view_bcp(cl(sc), B, C, P), B, C, P,
+    mu_cl, sc_cl = cl(mu), cl(sc)
+    check(lib().icm_gc_quantize_index(view_bcp(wide, B, C, P, 40), view_bcp(mu_cl, B, C, P), view_bcp(sc_cl, B, C, P), B, C, P,
                                       tab.data_ptr(), tab.numel(), 0.11, s2.data_ptr(), i2.data_ptr(), 2 * C * P, C * P,
                                       view_bcp(yh, B, C, P, 32), view_bcp(bf, B, C, P, 16), NULL_VIEW, stream_ptr()))
     assert torch.equal(s2[:, C * P:].reshape(B, C, H, W), sym)

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture()
 def eng():
     from compressai.models._engine import Engine
 
