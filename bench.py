@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- STF 768x512 compress+decompress throughput on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = compress + decompress of one batch of B synthetic 3x768x512 images per GPU (BASELINE.json
+configs[2] on each GPU; the batch shards across GPUs with no collective, weak scaling).  Prints ONE JSON line:
+
+  value         images/s, whole job, inputs and bit-streams resident in HBM (CUDA events, max over ranks)
+  e2e           the same metric through the public API with HOST buffers: pinned-host image -> H2D ->
+                model.compress -> Python `bytes` strings -> model.decompress(strings) -> x_hat -> D2H
+  roofline      dominant kernel family of a step (per-call CUDA events in a separate instrumented step)
+  cpu_baseline  the pinned CPU oracle (oracle/stf_ref.py + oracle/rans_oracle.c: the restatement of the
+                reference's path) on this box's host cores, on a bounded sample of the same workload
+  --impl reference   times only that CPU path (rank 0), same metric / config, and prints its own line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "image-compression-for-machine_b200"))
+sys.path.insert(1, REPO)
+
+import torch  # noqa: E402
+
+H_IMG, W_IMG = 768, 512
+SYMBOLS_PER_IMAGE = 589824 + 18432  # y + z
+FLOPS_PER_IMAGE = 609.9e9           # conv + linear + bmm, compress + decompress
+METRIC = "STF 768x512 compress+decompress images/s"
+
+
+def make_model(device):
+    """Reference-architecture STF with PyTorch-default random init (seed 0) plus the survey's rate-raising
+    tweak (SURVEY.md §8d 'stress weights'), so that the entropy coder sees many CDF tables and escapes
+    instead of the all-zero-index stream of plain random init."""
+    from compressai.zoo import models
+
+    torch.manual_seed(0)
+    m = models["stf"]()
+    with torch.no_grad():
+        m.layers[2].downsample.reduction.weight.mul_(8.0)
+        ramp = torch.exp(torch.linspace(math.log(0.05), math.log(30.0), 32))
+        for stack in m.cc_scale_transforms:
+            stack[8].bias.copy_(ramp)
+    m.update(force=True)
+    return m.to(device).eval()
+
+
+def make_images(batch, seed):
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.rand((batch, 3, H_IMG, W_IMG), generator=g)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_step(sd, x, tabs):
+    """One compress + decompress of the images in x on the host: the CPU restatement of the reference path."""
+    from oracle import stf_ref
+
+    c = stf_ref.compress(sd, x, gc_tab=tabs[0], eb_tab=tabs[1])
+    d = stf_ref.decompress(sd, c["strings"], c["shape"], gc_tab=tabs[0], eb_tab=tabs[1])
+    return c, d
+
+
+def cpu_baseline(model_sd, n_images, steps=1, warmup=0):
+    from oracle import entropy, stf_ref
+
+    sd = {k: v.detach().float().cpu() for k, v in model_sd.items()}
+    tabs = (entropy.gc_tables(), entropy.eb_tables(stf_ref.eb_params(sd)))
+    x = make_images(n_images, seed=0)
+    for _ in range(warmup):
+        cpu_reference_step(sd, x, tabs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(sd, x, tabs)
+    dt = (time.perf_counter() - t0) / steps
+    return n_images / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"stf 3x{H_IMG}x{W_IMG}, {args.batch} images per GPU per step (BASELINE.json configs[2]; batch sharded, no collective)"
+    config = {"workload": workload, "images_per_gpu": args.batch, "height": H_IMG, "width": W_IMG,
+              "weights": "random init seed 0 + rate-raising tweak (SURVEY.md 8d)", "l2": "inputs larger than L2 (302 MB per batch at B=64)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        mm = make_model("cpu")  # parameter container only; the timed path below is oracle/ on the CPU
+        ips, dt = cpu_baseline(mm.state_dict(), 1, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        cores = torch.get_num_threads()
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "1 image (3x768x512) compress+decompress per step, oracle/stf_ref.py fp32 + oracle/rans_oracle.c"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    from compressai import _native
+
+    model = make_model(dev)
+    B = args.batch
+    x_host = make_images(B, seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty((B, 3, H_IMG, W_IMG), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        c = model.compress(x_dev, device_strings=True)
+        return c, model.decompress(c["strings"], c["shape"])
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        c = model.compress(xd)                       # -> Python bytes on the host
+        d = model.decompress(c["strings"], c["shape"])
+        out_host.copy_(d["x_hat"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return c
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        l0 = _native.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = _native.launch_count() - l0
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, launches, r
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ms, launches, last = timed(step_device, args.steps)
+    clocks = sampler.stop() if sampler else None
+    c_last = last[0]
+    for packed, sizes in c_last["strings"]:  # deferred status check of the device-resident streams
+        if int(sizes.min()) < 0:
+            raise RuntimeError("rANS encoder reported an error status")
+    step_e2e()
+    ms_e2e, _, c_e2e = timed(step_e2e, args.steps)
+    n_img = B * world * args.steps
+    value = n_img / (ms / 1e3)
+    e2e_value = n_img / (ms_e2e / 1e3)
+    str_bytes = sum(len(s) for grp in c_e2e["strings"] for s in grp)
+    h2d = x_host.numel() * 4 + str_bytes
+    d2h = out_host.numel() * 4 + str_bytes
+
+    # instrumented step: per-entry-point CUDA events -> dominant kernel family and its roofline
+    roofline, families = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        with _native.Profile() as prof:
+            step_device()
+            summ = prof.summary()
+        total_ms = sum(v[1] for v in summ.values())
+        families = {k: {"calls": v[0], "ms": round(v[1], 3), "share": round(v[1] / total_ms, 4)} for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
+        calls, conv_ms, conv_flops = summ.get("icm_conv2d", (0, 0.0, 0.0))
+        dec_ms = summ.get("icm_rans_decoder_step", (0, 0.0, 0.0))[1]
+        enc_ms = summ.get("icm_rans_encode_batch", (0, 0.0, 0.0))[1]
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms else 0.0
+        roofline = {"kernel": "conv_igemm_kernel (icm_conv2d: all convolutions and linears)", "bound": "tensor", "achieved": round(ach, 2),
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                    "launches_per_step": calls, "avg_launch_us": round(conv_ms * 1e3 / max(calls, 1), 2),
+                    "algorithmic_flops_per_step": conv_flops, "share_of_step": round(conv_ms / total_ms, 4),
+                    "rans": {"decode_msym_s": round(B * 589824 / (dec_ms / 1e3) / 1e6, 1) if dec_ms else None,
+                             "encode_msym_s": round(B * SYMBOLS_PER_IMAGE / (enc_ms / 1e3) / 1e6, 1) if enc_ms else None,
+                             "streams_in_flight": B}}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, dt = cpu_baseline(model.state_dict(), 2, steps=1, warmup=0)
+        cpu = {"value": round(ips, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"2 images (3x768x512) compress+decompress once ({dt:.1f} s), oracle/stf_ref.py fp32 + oracle/rans_oracle.c"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 operands / fp32 accumulate (transforms); fp32 (entropy models); u64 (rANS)", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "families": families,
+            "msym_per_s": round(value * SYMBOLS_PER_IMAGE / 1e6, 2),
+            "bytes_per_image": round(str_bytes / B, 1),
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -34,9 +34,70 @@ class ConvArgs(C.Structure):
 
 
 _lib = None
+_profile = None  # a Profile instance while per-call CUDA-event timing is switched on (bench.py)
+
+
+class Profile:
+    """Wraps every device entry point with a CUDA-event pair on the current stream (bench.py's roofline
+    pass).  Usage: `with Profile() as p: model.compress(x)`; `p.summary()` -> {entry: (calls, ms, work)}."""
+
+    _HOST = {"icm_last_error", "icm_abi_version", "icm_launch_count", "icm_pmf_to_quantized_cdf", "icm_tables_create",
+             "icm_tables_destroy", "icm_rans_encode_workspace_bytes", "icm_rans_decoder_create", "icm_rans_decoder_destroy",
+             "icm_rans_decoder_set_streams", "icm_rans_decoder_status"}
+
+    def __init__(self):
+        self.records = {}
+        self._wrapped = {}
+
+    def __enter__(self):
+        global _profile
+        self._L = _load()
+        _profile = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._L, name)
+        if name in self._HOST or not name.startswith("icm_"):
+            return fn
+        w = self._wrapped.get(name)
+        if w is None:
+            def w(*args, _fn=fn, _name=name):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                rc = _fn(*args)
+                e.record()
+                self.records.setdefault(_name, []).append((s, e, self._work(_name, args)))
+                return rc
+            self._wrapped[name] = w
+        return w
+
+    @staticmethod
+    def _work(name, args):
+        if name == "icm_conv2d":  # algorithmic FLOPs: 2 * output pixels * Cout * taps * Cin
+            a = args[0]._obj
+            Ho = (a.H + 2 * a.pad - a.KH) // a.stride + 1
+            Wo = (a.W + 2 * a.pad - a.KW) // a.stride + 1
+            return 2.0 * a.B * Ho * Wo * a.Cout * a.KH * a.KW * a.Cin
+        return 0.0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            out[name] = (len(recs), sum(s.elapsed_time(e) for s, e, _ in recs), sum(w for _, _, w in recs))
+        return out
 
 
 def lib():
+    """The loaded library (or the profiling proxy while a Profile is active)."""
+    return _profile if _profile is not None else _load()
+
+
+def _load():
     """Load the library (building it first if nvcc is available and it is absent)."""
     global _lib
     if _lib is not None:
@@ -68,6 +129,7 @@ def lib():
         "icm_rans_decoder_create": (I, [I, C.POINTER(P)]),
         "icm_rans_decoder_destroy": (None, [P]),
         "icm_rans_decoder_set_streams": (I, [P, P, P, P, P]),
+        "icm_rans_decoder_set_streams_device": (I, [P, P, P, P]),
         "icm_rans_decoder_step": (I, [P, P, P, I64, P, P]),
         "icm_rans_decoder_status": (I, [P, P, P]),
         "icm_gc_quantize_index": (I, [View, View, View, I, I, I64, P, I, F, P, P, I64, I64, View, View, View, P]),
@@ -95,7 +157,7 @@ def lib():
 
 def check(rc, what=""):
     if rc is not None and rc < 0:
-        msg = lib().icm_last_error().decode(errors="replace")
+        msg = _load().icm_last_error().decode(errors="replace")
         raise NativeError(f"{what} failed ({rc}): {msg}")
     return rc
 
@@ -130,4 +192,4 @@ def view_nchw(t):
 
 
 def launch_count():
-    return int(lib().icm_launch_count())
+    return int(_load().icm_launch_count())

@@ -131,6 +131,11 @@ def encode_streams(tables, symbols, indexes, return_device=False):
     work = _workspace(L.icm_rans_encode_workspace_bytes(S, N), dev)
     sizes = torch.empty(S + 1, dtype=torch.int32, device=dev)
     cap = S * (2 * N + 64)  # 16 bit/symbol: ample for model data; retried at the worst case if exceeded
+    if return_device == "async":  # no host synchronisation: caller inspects `sizes` (negative = error code) later
+        packed = torch.empty(cap, dtype=torch.uint8, device=dev)
+        check(L.icm_rans_encode_batch(tables.handle, symbols.data_ptr(), indexes.data_ptr(), S, N, work.data_ptr(),
+                                      packed.data_ptr(), cap, sizes.data_ptr(), stream_ptr()), "icm_rans_encode_batch")
+        return packed, sizes
     for attempt in range(2):
         packed = torch.empty(cap, dtype=torch.uint8, device=dev)
         check(L.icm_rans_encode_batch(tables.handle, symbols.data_ptr(), indexes.data_ptr(), S, N, work.data_ptr(),
@@ -186,6 +191,14 @@ class StreamDecoder:
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         check(lib().icm_rans_decoder_set_streams(self.handle, self._bytes.data_ptr(), p(offsets), p(sizes), stream_ptr()),
               "icm_rans_decoder_set_streams")
+
+    def set_streams_device(self, packed, sizes):
+        """Streams as `encode_streams(..., return_device="async")` left them on the device (no host copy)."""
+        assert packed.is_cuda and sizes.is_cuda and sizes.dtype == torch.int32 and sizes.numel() >= self.n_streams
+        self._bytes = packed
+        self._sizes = sizes
+        check(lib().icm_rans_decoder_set_streams_device(self.handle, packed.data_ptr(), sizes.data_ptr(), stream_ptr()),
+              "icm_rans_decoder_set_streams_device")
 
     def decode_step(self, tables, indexes, out=None):
         """indexes: CUDA int32 [S, N] -> CUDA int32 [S, N] symbols."""

@@ -305,8 +305,11 @@ class SymmetricalTransFormer(CompressionModel):
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
 
     @torch.no_grad()
-    def compress(self, x):
-        """stf.py:671-732.  Returns {"strings": [[y_0..y_{B-1}], [z_0..z_{B-1}]], "shape": (h/4, w/4)}."""
+    def compress(self, x, device_strings=False):
+        """stf.py:671-732.  Returns {"strings": [[y_0..y_{B-1}], [z_0..z_{B-1}]], "shape": (h/4, w/4)}.
+
+        device_strings=True keeps the streams on the GPU: "strings" is then [(packed_y, sizes_y), (packed_z, sizes_z)]
+        (uint8 / int32 CUDA tensors, no host synchronisation), which decompress() accepts as is."""
         self._check_input(x)
         eb = self.entropy_bottleneck
         B = x.shape[0]
@@ -321,8 +324,9 @@ class SymmetricalTransFormer(CompressionModel):
               "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
         _, sym, idx = self._slice_loop("compress", B, h, w, mean_sup, scale_sup, y=y)
-        z_strings = ans.encode_streams(eb.device_tables(), z_sym, z_idx)
-        y_strings = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx)
+        mode = "async" if device_strings else False
+        z_strings = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device=mode)
+        y_strings = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device=mode)
         return {"strings": [y_strings, z_strings], "shape": torch.Size([zh, zw])}
 
     @torch.no_grad()
@@ -334,14 +338,15 @@ class SymmetricalTransFormer(CompressionModel):
         if dev.type != "cuda":
             raise NativeError("SymmetricalTransFormer runs on CUDA only (no CPU fallback)")
         y_strings, z_strings = strings
-        B = len(z_strings)
-        if len(y_strings) != B:
+        on_device = isinstance(z_strings, tuple)
+        B = z_strings[1].numel() - 1 if on_device else len(z_strings)
+        if not on_device and len(y_strings) != B:
             raise ValueError("need one y-string and one z-string per image")
         zh, zw = int(shape[0]), int(shape[1])
         Pz = zh * zw
         h, w = 4 * zh, 4 * zw
         zdec = ans.StreamDecoder(B)
-        zdec.set_streams(z_strings)
+        zdec.set_streams_device(*z_strings) if on_device else zdec.set_streams(z_strings)
         z_idx = torch.arange(192, dtype=torch.int32, device=dev).repeat_interleave(Pz).repeat(B, 1)
         z_sym = zdec.decode_step(eb.device_tables(), z_idx)
         z_hat = torch.empty((B * Pz, 192), dtype=torch.bfloat16, device=dev)
@@ -349,8 +354,9 @@ class SymmetricalTransFormer(CompressionModel):
                                    NULL_VIEW, view_bcp(z_hat, B, 192, Pz), NULL_VIEW, stream_ptr()), "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
         ydec = ans.StreamDecoder(B)
-        ydec.set_streams(y_strings)
+        ydec.set_streams_device(*y_strings) if on_device else ydec.set_streams(y_strings)
         y_hat, _, _ = self._slice_loop("decompress", B, h, w, mean_sup, scale_sup, decoder=ydec)
-        zdec.check_status()
-        ydec.check_status()
+        if not on_device:  # (status is a host read; the device-resident path leaves it to the caller)
+            zdec.check_status()
+            ydec.check_status()
         return {"x_hat": self._synthesis(y_hat, B, h, w, clamp=True)}

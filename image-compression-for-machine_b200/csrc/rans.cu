@@ -203,6 +203,29 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const Record *__restric
     }
 }
 
+// device-side set_streams: word offsets / lengths from the encoder's int32 byte sizes (exclusive scan, one warp)
+__global__ void rans_set_streams_kernel(const int32_t *__restrict__ sizes, int n_streams, int64_t *__restrict__ pos,
+                                        int64_t *__restrict__ word_off, int64_t *__restrict__ nwords, int32_t *__restrict__ status)
+{
+    long long run = 0;
+    for (int base = 0; base < n_streams; base += 32) {
+        const int i = base + threadIdx.x;
+        const long long v = (i < n_streams && sizes[i] > 0) ? sizes[i] / 4 : 0;
+        long long incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)threadIdx.x >= d) incl += o;
+        }
+        if (i < n_streams) {
+            word_off[i] = run + incl - v;
+            nwords[i] = v;
+            pos[i] = -1;
+            status[i] = sizes[i] < 0 ? sizes[i] : 0;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
 // (3) pack: exclusive scan of sizes (one warp) + copy
 __global__ void rans_scan_kernel(const int32_t *__restrict__ sizes, int n_streams, long long *__restrict__ offsets,
                                  int32_t *__restrict__ total_out)
@@ -542,6 +565,16 @@ extern "C" int icm_rans_decoder_set_streams(icm_rans_decoder *d, const uint8_t *
     ICM_CUDA(cudaMemcpyAsync(d->d_pos, host.data(), host.size() * 8, cudaMemcpyHostToDevice, st));
     ICM_CUDA(cudaMemsetAsync(d->d_status, 0, (size_t)n * 4, st));
     ICM_CUDA(cudaStreamSynchronize(st)); // `host` is pageable and dies with this frame
+    d->d_words = (const uint32_t *)d_bytes;
+    return ICM_OK;
+}
+
+extern "C" int icm_rans_decoder_set_streams_device(icm_rans_decoder *d, const uint8_t *d_bytes, const int32_t *d_sizes, void *stream)
+{
+    ICM_CHECK_ARG(d && d_bytes && d_sizes, "icm_rans_decoder_set_streams_device: null argument");
+    ICM_CHECK_ARG(((uintptr_t)d_bytes & 3) == 0, "icm_rans_decoder_set_streams_device: byte buffer must be 4-byte aligned");
+    rans_set_streams_kernel<<<1, 32, 0, as_stream(stream)>>>(d_sizes, d->n_streams, d->d_pos, d->d_word_off, d->d_nwords, d->d_status);
+    ICM_LAUNCH_CHECK();
     d->d_words = (const uint32_t *)d_bytes;
     return ICM_OK;
 }
