@@ -37,19 +37,22 @@ FLOPS_PER_IMAGE = 609.9e9           # conv + linear + bmm, compress + decompress
 METRIC = "STF 768x512 compress+decompress images/s"
 
 
-def make_model(device):
-    """Reference-architecture STF with PyTorch-default random init (seed 0) plus the survey's rate-raising
-    tweak (SURVEY.md §8d 'stress weights'), so that the entropy coder sees many CDF tables and escapes
-    instead of the all-zero-index stream of plain random init."""
+WEIGHTS = {"default": "PyTorch default init under torch.manual_seed(0) (the reference constructor's effective init, SURVEY.md 8d)",
+           "stress": "default init + the survey's rate-raising tweak (SURVEY.md 8d: many CDF tables, ~26% escape symbols)"}
+
+
+def make_model(device, weights="default"):
+    """Reference-architecture STF, random weights (no checkpoint ships with the reference)."""
     from compressai.zoo import models
 
     torch.manual_seed(0)
     m = models["stf"]()
-    with torch.no_grad():
-        m.layers[2].downsample.reduction.weight.mul_(8.0)
-        ramp = torch.exp(torch.linspace(math.log(0.05), math.log(30.0), 32))
-        for stack in m.cc_scale_transforms:
-            stack[8].bias.copy_(ramp)
+    if weights == "stress":
+        with torch.no_grad():
+            m.layers[2].downsample.reduction.weight.mul_(8.0)
+            ramp = torch.exp(torch.linspace(math.log(0.05), math.log(30.0), 32))
+            for stack in m.cc_scale_transforms:
+                stack[8].bias.copy_(ramp)
     m.update(force=True)
     return m.to(device).eval()
 
@@ -120,6 +123,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--weights", default="default", choices=sorted(WEIGHTS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -127,12 +131,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"stf 3x{H_IMG}x{W_IMG}, {args.batch} images per GPU per step (BASELINE.json configs[2]; batch sharded, no collective)"
     config = {"workload": workload, "images_per_gpu": args.batch, "height": H_IMG, "width": W_IMG,
-              "weights": "random init seed 0 + rate-raising tweak (SURVEY.md 8d)", "l2": "inputs larger than L2 (302 MB per batch at B=64)"}
+              "weights": WEIGHTS[args.weights], "l2": "inputs larger than L2 (302 MB per batch at B=64)"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        mm = make_model("cpu")  # parameter container only; the timed path below is oracle/ on the CPU
+        mm = make_model("cpu", args.weights)  # parameter container only; the timed path below is oracle/ on the CPU
         ips, dt = cpu_baseline(mm.state_dict(), 1, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         cores = torch.get_num_threads()
         print(json.dumps({
@@ -158,7 +162,7 @@ def main():
         dist = dist_mod
     from compressai import _native
 
-    model = make_model(dev)
+    model = make_model(dev, args.weights)
     B = args.batch
     x_host = make_images(B, seed=rank).pin_memory()
     x_dev = x_host.to(dev)

@@ -56,12 +56,16 @@ struct icm_rans_decoder {
 namespace icm {
 
 // ------------------------------------------------------------------------------------------------
-// (1) records
+// (1) records.  One 16-byte record per symbol drives a branch-free state update
+//        if (hi32(x) >= thi) { emit lo32(x); x >>= 32; }          thi = freq << 15  (x_max = freq << 47)
+//        q = mulhi64(x, rcp) >> shift;  x += bias + q * cmpl;      cmpl = 2^16 - freq
+//     which equals Rans64EncPut's  x = (x / freq << 16) + x % freq + start  (rans64.h:167-278).
 struct __align__(16) Record {
     uint32_t rcp_lo, rcp_hi; // fixed-point reciprocal of freq (rans64.h:223-241)
-    uint32_t meta;           // freq[0..16] | rcp_shift[17..21] | bypass[22]
+    uint32_t meta;           // cmpl[0..16] | rcp_shift[17..20] | bypass[21] | nibbles[24..27]
     uint32_t bias;           // start (freq >= 2) or start + 65535 (freq == 1)
 };
+constexpr uint32_t kRecBypass = 1u << 21;
 
 __global__ void __launch_bounds__(256) rans_records_kernel(TablesDev T, const int32_t *__restrict__ sym,
                                                            const int32_t *__restrict__ idx, long long n_total,
@@ -85,58 +89,70 @@ __global__ void __launch_bounds__(256) rans_records_kernel(TablesDev T, const in
         const uint32_t start = (uint16_t)cdf[v];
         const uint32_t freq = (uint16_t)(cdf[v + 1] - cdf[v]);
         Record r;
+        uint32_t shift_m1 = 0;
         if (freq < 2) { // rans64.h:192-221
             r.rcp_lo = 0xFFFFFFFFu; r.rcp_hi = 0xFFFFFFFFu;
-            r.meta = freq;
             r.bias = start + (1u << kPrecision) - 1;
         } else {
-            uint32_t shift = 32 - __clz(freq - 1); // ceil(log2(freq))
-            uint64_t x1 = 1ull << (shift + 31);
-            uint64_t t1 = x1 / freq;
-            uint64_t x0 = (uint64_t)(freq - 1) + ((x1 % freq) << 32);
-            uint64_t t0 = x0 / freq;
-            uint64_t rcp = t0 + (t1 << 32);
+            const uint32_t shift = 32 - __clz(freq - 1); // ceil(log2(freq))
+            const uint64_t x1 = 1ull << (shift + 31);
+            const uint64_t t1 = x1 / freq;
+            const uint64_t x0 = (uint64_t)(freq - 1) + ((x1 % freq) << 32);
+            const uint64_t t0 = x0 / freq;
+            const uint64_t rcp = t0 + (t1 << 32);
             r.rcp_lo = (uint32_t)rcp; r.rcp_hi = (uint32_t)(rcp >> 32);
-            r.meta = freq | ((shift - 1) << 17);
+            shift_m1 = shift - 1;
             r.bias = start;
         }
-        if (v == max_value) r.meta |= 1u << 22;
+        r.meta = ((1u << kPrecision) - freq) | (shift_m1 << 17);
+        if (v == max_value) {
+            uint32_t nb = 0;
+            while (nb < 8 && (raw >> (nb * 4)) != 0) ++nb;
+            r.meta |= kRecBypass | (nb << 24);
+        }
         rec[i] = r;
         raw_out[i] = raw;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// (2) serial walk, one warp per stream
+// (2) serial walk, one warp per stream.  Every lane carries the state (warp-uniform control flow); the
+// records of 32 symbols are staged in shared memory (double buffered, next chunk's global loads in flight)
+// and read back with one broadcast LDS.128 per symbol, issued one symbol ahead of its use.  Emitted words
+// go to a 128-word shared ring (one predicated store, no branch) that is drained 128 B at a time between
+// chunks; a symbol emits at most two words (<= 52 bits of payload), so a chunk emits at most 65.
+constexpr int kRing = 128;
+
 struct Emitter {
-    uint32_t hold;     // the word this lane keeps until the warp has 32 of them
-    uint32_t count;    // words emitted so far (warp-uniform)
-    uint32_t *top;     // one past the last word of the stream's scratch area
-    uint32_t capacity; // words
-    bool overflow;
-    int lane;
-    __device__ __forceinline__ void put(uint32_t w)
+    uint32_t *ring;
+    uint32_t count, flushed; // words emitted / words already stored to global (warp-uniform)
+    uint32_t *top;           // one past the last word of the stream's scratch area
+    uint32_t capacity, overflow, lane;
+    __device__ __forceinline__ void put_if(bool emit, uint32_t w)
     {
-        if ((count & 31u) == (uint32_t)lane) hold = w;
-        ++count;
-        if ((count & 31u) == 0) {
-            if (count <= capacity) *(top - 1 - (count - 32 + lane)) = hold; // 128 B, descending addresses
-            else overflow = true;
-        }
+        if (emit) ring[count & (kRing - 1)] = w; // every lane stores the same word: uniform, one transaction
+        count += emit ? 1u : 0u;
     }
-    __device__ __forceinline__ void finish()
+    __device__ __forceinline__ void drain(bool all)
     {
-        const uint32_t rem = count & 31u;
-        if (rem) {
-            if (count <= capacity) { if ((uint32_t)lane < rem) *(top - 1 - (count - rem + lane)) = hold; }
-            else overflow = true;
+        __syncwarp();
+        while (count - flushed >= 32u || (all && count != flushed)) {
+            const uint32_t e = flushed + lane;
+            if (e < count) {
+                if (e < capacity) *(top - 1 - e) = ring[e & (kRing - 1)]; // descending addresses, 128 B per pass
+                else overflow = 1;
+            }
+            flushed = min(flushed + 32u, count);
         }
+        __syncwarp();
     }
 };
 
 __device__ __forceinline__ void put_bits4(uint64_t &x, uint32_t val, Emitter &e)
 { // Rans64EncPutBits with nbits = 4: freq = 2^12, x_max = 2^59
-    if (x >= (1ull << 59)) { e.put((uint32_t)x); x >>= 32; }
+    const bool emit = (uint32_t)(x >> 32) >= (1u << 27);
+    e.put_if(emit, (uint32_t)x);
+    x = emit ? (x >> 32) : x;
     x = (x << 4) | val;
 }
 
@@ -146,59 +162,68 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const Record *__restric
                                                          long long cap_words, int32_t *__restrict__ sizes,
                                                          const int32_t *__restrict__ status)
 {
+    __shared__ uint4 s_rec[2][32];
+    __shared__ uint32_t s_raw[2][32];
+    __shared__ uint32_t s_ring[kRing];
     const int s = blockIdx.x, lane = threadIdx.x;
-    const Record *R = rec + (size_t)s * n_per_stream;
+    const uint4 *R = reinterpret_cast<const uint4 *>(rec + (size_t)s * n_per_stream);
     const uint32_t *RAW = raw_in + (size_t)s * n_per_stream;
     Emitter e;
-    e.hold = 0; e.count = 0; e.lane = lane; e.overflow = false;
+    e.ring = s_ring; e.count = 0; e.flushed = 0; e.lane = lane; e.overflow = 0;
     e.top = words + (size_t)(s + 1) * cap_words;
     e.capacity = (uint32_t)cap_words;
     uint64_t x = kRansL;
 
     const long long n_chunks = (n_per_stream + 31) / 32;
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-    uint32_t cur_raw = 0, nxt_raw = 0;
-    {
-        long long j = (n_chunks - 1) * 32 + lane;
-        if (n_chunks > 0 && j < n_per_stream) { nxt = *reinterpret_cast<const uint4 *>(R + j); nxt_raw = RAW[j]; }
+    uint4 g = make_uint4(0, 0, 0, 0);
+    uint32_t graw = 0;
+    if (n_chunks > 0) {
+        const long long j = (n_chunks - 1) * 32 + lane;
+        if (j < n_per_stream) { g = __ldg(R + j); graw = __ldg(RAW + j); }
     }
     for (long long c = n_chunks - 1; c >= 0; --c) {
-        cur = nxt; cur_raw = nxt_raw;
-        if (c > 0) { // prefetch the next (earlier) chunk while this one is being coded
-            long long j = (c - 1) * 32 + lane;
-            nxt = *reinterpret_cast<const uint4 *>(R + j);
-            nxt_raw = RAW[j];
+        const int buf = (int)(c & 1);
+        s_rec[buf][lane] = g;
+        s_raw[buf][lane] = graw;
+        if (c > 0) { // the next (earlier) chunk's loads fly while this one is coded
+            const long long j = (c - 1) * 32 + lane;
+            g = __ldg(R + j);
+            graw = __ldg(RAW + j);
         }
+        e.drain(false); // also orders the staging stores above before the reads below
         const int valid = (int)min(32LL, n_per_stream - c * 32);
+        uint4 cur = s_rec[buf][valid - 1];
+#pragma unroll 1
         for (int k = valid - 1; k >= 0; --k) {
-            const uint32_t rcp_lo = __shfl_sync(0xffffffffu, cur.x, k);
-            const uint32_t rcp_hi = __shfl_sync(0xffffffffu, cur.y, k);
-            const uint32_t meta = __shfl_sync(0xffffffffu, cur.z, k);
-            const uint32_t bias = __shfl_sync(0xffffffffu, cur.w, k);
-            if (meta & (1u << 22)) {
-                // records of a bypass symbol, in push order: main, unary(n), nibble_0..nibble_{n-1};
-                // drained back to front
-                const uint32_t raw = __shfl_sync(0xffffffffu, cur_raw, k);
-                int nb = 0;
-                while (nb < 8 && (raw >> (nb * 4)) != 0) ++nb;
+            const uint4 nxt = s_rec[buf][k > 0 ? k - 1 : 0];
+            if (cur.z & kRecBypass) {
+                // records of an escaped symbol, in push order: main, count(nb), nibble_0..nibble_{nb-1};
+                // drained back to front.  nb <= 8 < 15, so the count is a single nibble.
+                const uint32_t raw = s_raw[buf][k];
+                const int nb = (int)((cur.z >> 24) & 15u);
+#pragma unroll 1
                 for (int j = nb - 1; j >= 0; --j) put_bits4(x, (raw >> (j * 4)) & 15u, e);
-                // unary count: pushed as 15,15,...,(nb mod-ish); nb <= 8 < 15 so a single chunk
                 put_bits4(x, (uint32_t)nb, e);
             }
-            const uint32_t freq = meta & 0x1FFFFu;
-            const uint32_t shift = (meta >> 17) & 31u;
-            if (x >= ((uint64_t)freq << 47)) { e.put((uint32_t)x); x >>= 32; }
-            const uint64_t rcp = ((uint64_t)rcp_hi << 32) | rcp_lo;
+            const uint32_t cmpl = cur.z & 0x1FFFFu;
+            const uint32_t shift = (cur.z >> 17) & 15u;
+            const uint32_t thi = ((1u << kPrecision) - cmpl) << 15;
+            const bool emit = (uint32_t)(x >> 32) >= thi;
+            e.put_if(emit, (uint32_t)x);
+            x = emit ? (x >> 32) : x;
+            const uint64_t rcp = ((uint64_t)cur.y << 32) | cur.x;
             const uint64_t q = __umul64hi(x, rcp) >> shift;
-            x = x + bias + q * (uint64_t)((1u << kPrecision) - freq);
+            x = x + cur.w + q * (uint64_t)cmpl;
+            cur = nxt;
         }
     }
     // Rans64EncFlush: ptr -= 2; ptr[0] = lo; ptr[1] = hi  => hi is the "earlier" emitted word
-    e.put((uint32_t)(x >> 32));
-    e.put((uint32_t)x);
-    e.finish();
+    e.drain(false);
+    e.put_if(true, (uint32_t)(x >> 32));
+    e.put_if(true, (uint32_t)x);
+    e.drain(true);
     if (lane == 0) {
-        int32_t st = status[s];
+        const int32_t st = status[s];
         sizes[s] = st < 0 ? st : (e.overflow ? ICM_ERR_CAPACITY : (int32_t)(e.count * 4));
     }
 }
@@ -263,7 +288,20 @@ __global__ void __launch_bounds__(256) rans_pack_kernel(const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// decoder
+// decoder: one warp per stream.  Per-symbol critical path (all lanes carry x):
+//     cum = x & 0xFFFF -> 32 lanes compare one CDF entry each -> ballot -> ffs -> every lane has already
+//     formed freq * (x >> 16) + cum - start for ITS entry; the winner's 64-bit result is shuffled out -> renorm.
+// Everything else is taken off that path: the table of symbol k+1 is known in advance (indexes are an
+// input), so its metadata and a speculative 32-entry window of its CDF row (the whole row for tables with
+// <= 32 entries, else the 32 entries around the distribution's centre) are loaded from shared memory while
+// symbol k is decoded.  Only when cum falls outside that window does the coder take the general route:
+// the per-table "cum >> (16-k) -> first candidate" table, then 32-entry windows until one brackets cum.
+__device__ __forceinline__ uint32_t cdf_window(const uint16_t *s_cdf, uint32_t base, int size, int s0, int lane)
+{
+    const int cand = s0 + lane;
+    return (cand >= size - 1) ? 0x10000u : (uint32_t)s_cdf[base + cand]; // entry size-1 is 65536 by definition
+}
+
 __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint32_t *__restrict__ words,
                                                          const int64_t *__restrict__ word_off,
                                                          const int64_t *__restrict__ nwords_arr,
@@ -274,9 +312,8 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *s_cdf = reinterpret_cast<uint16_t *>(smem_raw);
     uint16_t *s_lut = s_cdf + ((T.total16 + 7) & ~7);
-    int32_t *s_base = reinterpret_cast<int32_t *>(s_lut + ((size_t)T.n_cdf << T.lut_bits));
-    int32_t *s_size = s_base + T.n_cdf;
-    int32_t *s_off = s_size + T.n_cdf;
+    uint4 *s_meta = reinterpret_cast<uint4 *>(s_lut + ((size_t)T.n_cdf << T.lut_bits)); // {base, size | t << 16, offset, s0}
+    __shared__ uint4 s_sym[2][32];
     const int lane = threadIdx.x;
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(T.cdf16);
@@ -285,7 +322,12 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint
         const uint4 *gl = reinterpret_cast<const uint4 *>(T.lut);
         uint4 *dl = reinterpret_cast<uint4 *>(s_lut);
         for (int i = lane; i < (int)(((size_t)T.n_cdf << T.lut_bits) / 8); i += 32) dl[i] = gl[i];
-        for (int i = lane; i < T.n_cdf; i += 32) { s_base[i] = T.base[i]; s_size[i] = T.sizes[i]; s_off[i] = T.offsets[i]; }
+        for (int i = lane; i < T.n_cdf; i += 32) {
+            const int size = T.sizes[i], off = T.offsets[i];
+            int s0 = 0;
+            if (size > 32) { s0 = -off - 15; s0 = max(0, min(s0, size - 32)); }
+            s_meta[i] = make_uint4((uint32_t)T.base[i], (uint32_t)size | ((uint32_t)i << 16), (uint32_t)off, (uint32_t)s0);
+        }
     }
     __syncwarp();
 
@@ -304,76 +346,112 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint
     // word window: lane l of wcur holds word (wblock*32 + l); wnxt is the following block
     long long wblock = pos >> 5;
     auto load_block = [&](long long b) -> uint32_t {
-        long long j = b * 32 + lane;
-        return j < nwords ? W[j] : 0u; // past-the-end reads are UB in the reference; we feed zeros
+        const long long j = b * 32 + lane;
+        return j < nwords ? __ldg(W + j) : 0u; // past-the-end reads are UB in the reference; we feed zeros
     };
     uint32_t wcur = load_block(wblock), wnxt = load_block(wblock + 1);
-    auto next_word = [&]() -> uint32_t {
-        const uint32_t w = __shfl_sync(0xffffffffu, wcur, (int)(pos & 31));
-        ++pos;
-        if ((pos & 31) == 0) { wcur = wnxt; ++wblock; wnxt = load_block(wblock + 1); }
-        return w;
+    uint32_t wv = __shfl_sync(0xffffffffu, wcur, (int)(pos & 31)); // the next stream word, always kept ready
+    // renormalise (Rans64DecAdvance tail / Rans64DecGetBits tail): predicated, plus a rare window refill
+    auto renorm = [&]() {
+        const bool rn = x < kRansL;
+        x = rn ? ((x << 32) | wv) : x;
+        pos += rn ? 1 : 0;
+        if (rn && (pos & 31) == 0) { wcur = wnxt; ++wblock; wnxt = load_block(wblock + 1); }
+        wv = __shfl_sync(0xffffffffu, wcur, (int)(pos & 31));
     };
     auto get4 = [&]() -> int {
         const int val = (int)(x & 15u);
         x >>= 4;
-        if (x < kRansL) x = (x << 32) | next_word();
+        renorm();
         return val;
     };
 
     const int32_t *I = idx + (size_t)s * n_per_stream;
     int32_t *O = out + (size_t)s * n_per_stream;
     const int lut_shift = kPrecision - T.lut_bits;
+    const long long n = n_per_stream;
+    const long long n_chunks = (n + 31) / 32;
     bool bad = false;
-    const long long n_chunks = (n_per_stream + 31) / 32;
-    int inxt = (lane < n_per_stream) ? I[lane] : 0;
+    auto meta_of = [&](int t) -> uint4 {
+        if (t < 0 || t >= T.n_cdf) { bad = true; t = 0; }
+        return s_meta[t];
+    };
+    auto sym_at = [&](long long g) -> uint4 {
+        g = min(g, n - 1);
+        return s_sym[(g >> 5) & 1][g & 31];
+    };
+    int ireg = (lane < n) ? __ldg(I + lane) : 0;
+    s_sym[0][lane] = meta_of(ireg);
+    ireg = (32 + lane < n) ? __ldg(I + 32 + lane) : 0;
+    __syncwarp();
+    uint4 meta0 = sym_at(0), meta1 = sym_at(1);
+    uint32_t v0 = cdf_window(s_cdf, meta0.x, (int)(meta0.y & 0xFFFFu), (int)meta0.w, lane);
+    uint32_t f0 = __shfl_down_sync(0xffffffffu, v0, 1) - v0;
+
     for (long long c = 0; c < n_chunks; ++c) {
-        const int icur = inxt;
-        {
-            long long j = (c + 1) * 32 + lane;
-            inxt = (j < n_per_stream) ? I[j] : 0;
+        __syncwarp();
+        if (c + 1 < n_chunks) { // stage the next chunk's per-symbol metadata; its indexes were fetched a chunk ago
+            s_sym[(c + 1) & 1][lane] = meta_of(ireg);
+            const long long j = (c + 2) * 32 + lane;
+            ireg = (j < n) ? __ldg(I + j) : 0;
         }
-        const int valid = (int)min(32LL, n_per_stream - c * 32);
+        __syncwarp();
+        const int valid = (int)min(32LL, n - c * 32);
         int result = 0;
+#pragma unroll 1
         for (int k = 0; k < valid; ++k) {
-            int t = __shfl_sync(0xffffffffu, icur, k);
-            if (t < 0 || t >= T.n_cdf) { bad = true; t = 0; }
-            const int size = s_size[t];
-            const int base = s_base[t];
+            const long long gk = c * 32 + k;
+            // ---- off the critical path: operands of the next two symbols, the next stream word
+            const uint32_t v1 = cdf_window(s_cdf, meta1.x, (int)(meta1.y & 0xFFFFu), (int)meta1.w, lane);
+            const uint4 meta2 = sym_at(gk + 2);
+            const int size = (int)(meta0.y & 0xFFFFu);
+            // ---- critical path
             const uint32_t cum = (uint32_t)x & 0xFFFFu;
-            int s0 = s_lut[(t << T.lut_bits) + (cum >> lut_shift)];
-            uint32_t start, next;
-            int symbol;
-            while (true) {
-                const int cand = s0 + lane;
-                const uint32_t v = (cand >= size - 1) ? 0x10000u : (uint32_t)s_cdf[base + cand];
-                const uint32_t m = __ballot_sync(0xffffffffu, v > cum);
-                if (m == 0) { s0 += 31; continue; } // more than 31 symbols inside this bucket
-                const int p = __ffs(m) - 1;          // p >= 1: entry s0 is <= cum by construction
-                start = __shfl_sync(0xffffffffu, v, p - 1);
-                next = __shfl_sync(0xffffffffu, v, p);
-                symbol = s0 + p - 1;
-                break;
+            uint32_t vv = v0, ff = f0;
+            int s0 = (int)meta0.w;
+            uint32_t m = __ballot_sync(0xffffffffu, vv > cum);
+            if ((m & 1u) | (m == 0u)) { // cum is outside the speculative window
+                const int t = (int)(meta0.y >> 16);
+                s0 = s_lut[(t << T.lut_bits) + (cum >> lut_shift)];
+                while (true) {
+                    vv = cdf_window(s_cdf, meta0.x, size, s0, lane);
+                    m = __ballot_sync(0xffffffffu, vv > cum);
+                    if (m != 0u) break;
+                    s0 += 31; // more than 31 symbols share this bucket
+                }
+                ff = __shfl_down_sync(0xffffffffu, vv, 1) - vv;
             }
-            // Rans64DecAdvance
-            x = (uint64_t)(next - start) * (x >> kPrecision) + cum - start;
-            if (x < kRansL) x = (x << 32) | next_word();
+            const int p = __ffs(m) - 1; // >= 1: entry s0 is <= cum
+            // Rans64DecAdvance, formed by every lane for its own entry; lane p-1 holds the real one
+            const uint64_t nx = (uint64_t)ff * (x >> kPrecision) + (uint64_t)(cum - vv);
+            const uint32_t nlo = __shfl_sync(0xffffffffu, (uint32_t)nx, p - 1);
+            const uint32_t nhi = __shfl_sync(0xffffffffu, (uint32_t)(nx >> 32), p - 1);
+            x = ((uint64_t)nhi << 32) | nlo;
+            renorm();
+            const int symbol = s0 + p - 1;
             int value = symbol;
-            const int max_value = size - 2;
-            if (symbol == max_value) { // bypass escape
+            if (symbol == size - 2) { // bypass escape
+                const int max_value = size - 2;
                 int val = get4();
                 int nb = val;
+#pragma unroll 1
                 while (val == 15) { val = get4(); nb += val; }
                 int raw = 0;
+#pragma unroll 1
                 for (int j = 0; j < nb; ++j) { val = get4(); raw |= val << ((j * 4) & 31); }
                 value = raw >> 1;
                 if (raw & 1) value = -value - 1; else value += max_value;
             }
-            value += s_off[t];
+            value += (int)meta0.z;
             if (lane == k) result = value;
+            // ---- rotate the pipeline
+            meta0 = meta1; meta1 = meta2;
+            v0 = v1;
+            f0 = __shfl_down_sync(0xffffffffu, v1, 1) - v1;
         }
         if (lane < valid) O[c * 32 + lane] = result;
     }
+    bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
         state[s] = x;
         pos_arr[s] = pos;
@@ -406,7 +484,7 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
     }
     int lut_bits = 8;
     auto smem_need = [&](int bits) {
-        return (size_t)((total + 7) & ~7) * 2 + ((size_t)n_cdf << bits) * 2 + (size_t)n_cdf * 12;
+        return (size_t)((total + 7) & ~7) * 2 + ((size_t)n_cdf << bits) * 2 + (size_t)n_cdf * 16;
     };
     while (lut_bits > 3 && smem_need(lut_bits) > 200 * 1024) --lut_bits;
     ICM_CHECK_ARG(smem_need(lut_bits) <= 200 * 1024, "icm_tables_create: tables too large for shared memory");
