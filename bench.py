@@ -161,6 +161,7 @@ def main():
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     from compressai import _native
+    from compressai.utils.sharding import max_over_ranks
 
     model = make_model(dev, args.weights)
     B = args.batch
@@ -197,10 +198,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = _native.launch_count() - l0
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms, device=dev)
         barrier()
         return ms, launches, r
 

@@ -8,8 +8,11 @@
 //              is TMA's out-of-bounds zero fill, stride-2 convolutions use the tensor map's element strides)
 //              and one 2-D box of the packed weights, both landing 128B-swizzled in shared memory;
 //   warp 1     allocates TMEM and issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM);
-//   warps 2-5  epilogue: tcgen05.ld the accumulator rows, bias + activation (+ residual) in registers,
-//              vectorised stores (optionally with the PixelShuffle permutation folded into the address).
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating 16-column chunks): tcgen05.ld the
+//              accumulator rows, bias + activation (+ residual) in registers, vectorised stores (optionally
+//              with the PixelShuffle permutation folded into the address).
+// Shared memory and TMEM are sized so that two (small-K layers: up to four) CTAs share an SM: the epilogue of
+// one tile then overlaps the loads and MMAs of another, which is what the memory-bound Swin linears need.
 // The K loop order (tap-major, then 64-channel chunks) is fixed and there is no split-K, so every output
 // element is reduced in the same order whatever the batch size or tile shape: the encoder and decoder
 // sides of the codec see bit-identical means/scales (SURVEY.md §7 "Encoder/decoder determinism").
@@ -120,15 +123,38 @@ struct ConvParams {
     void *out;
 };
 
+// exact-form GELU 0.5 v (1 + erf(v / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
+// below the bf16 rounding of the stored activation): 2 MUFU + ~10 FMA instead of libdevice erff's ~30
+// instructions -- the epilogue of the GELU linears is otherwise ALU-bound.
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float gelu_erf(float v)
+{
+    const float u = fabsf(v) * 0.70710678118654752440f;
+    const float t = mufu_rcp(fmaf(0.3275911f, u, 1.0f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(t, poly, 1.421413741f);
+    poly = fmaf(t, poly, -0.284496736f);
+    poly = fmaf(t, poly, 0.254829592f);
+    poly *= t;
+    const float e = mufu_ex2(-1.4426950408889634f * u * u);
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    const float h = 0.5f * v;
+    return fmaf(fabsf(h), erf_abs, h); // v * erf(v / sqrt 2) is even in v
+}
+
 __device__ __forceinline__ float apply_act(float v, int act)
 {
-    if (act == ICM_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    if (act == ICM_ACT_GELU) return gelu_erf(v);
     if (act == ICM_ACT_HALF_TANH) return 0.5f * tanhf(v);
     if (act == ICM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
     return v;
 }
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int CONV_THREADS = 320; // TMA warp + MMA warp + 8 epilogue warps
+
+__global__ void __launch_bounds__(CONV_THREADS, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -209,8 +235,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3; // TMEM lane quarter this warp may read
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        const int q = warp & 3;          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2; // the two warps of a quarter take alternate column chunks
         const int r = q * 32 + lane;
         const int th = r >> p.TW_log2, tw = r & (TW - 1);
         const int oh = h0 + th, ow = w0 + tw;
@@ -219,7 +246,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
         const int Cq = p.pixel_shuffle ? p.Cout / (p.pixel_shuffle * p.pixel_shuffle) : 0;
-        for (int c16 = 0; c16 < p.BN / 16; ++c16) {
+        for (int c16 = half; c16 < p.BN / 16; c16 += 2) {
             uint32_t acc[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c16 * 16), acc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -370,10 +397,13 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     const int k_iters = p.KH * p.KW * p.k_chunks;
     const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-    p.stages = (int)((200 * 1024) / stage_bytes);
+    // pipeline depth: never deeper than the K loop; capped so that at least two CTAs fit on an SM
+    // (227 KB shared memory, 512 TMEM columns, 2 x 320 threads)
+    // Long K loops (the 3x3 / 5x5 convolutions) are MMA-bound: give one CTA the whole SM and a deep pipeline.
+    p.stages = (int)(((k_iters >= 16 ? 200 : 110) * 1024) / stage_bytes);
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages > k_iters) p.stages = k_iters;
-    if (p.stages < 1) p.stages = 1;
+    if (p.stages < 2) p.stages = k_iters < 2 ? 1 : 2;
     p.act = a->act; p.out_dtype = a->out_dtype; p.pixel_shuffle = ps;
     p.out_pitch = a->out_pitch; p.res_pitch = a->res_pitch;
     p.bias = a->bias; p.residual = a->residual; p.out = a->out;
@@ -412,7 +442,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     }
     ICM_CHECK_ARG(m_tiles <= 0x7FFFFFFF, "icm_conv2d: too many tiles");
     dim3 grid((unsigned)m_tiles, (a->Cout + p.BN - 1) / p.BN);
-    conv_igemm_kernel<<<grid, 192, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
+    conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }

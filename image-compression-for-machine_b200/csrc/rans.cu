@@ -1,19 +1,27 @@
 // rANS coder on the GPU: the reference's 64-bit-state, 32-bit-renormalising coder, one state per
 // stream, bit-exact with compressai.ans (R1-R4 of SURVEY.md §8a; ryg rans64.h:59-142).
 //
+// A stream is a strictly serial recurrence, so its speed is (instructions per symbol) x (issue latency of a
+// lone warp, ~3.6 cycles measured on B200).  Both coders are therefore written to keep the per-symbol
+// instruction count minimal and branch-free on the common path; everything that does not depend on the
+// coder state is precomputed in parallel or fetched ahead of its use.
+//
 // Encoder = three kernels
-//   (1) rans_records_kernel   embarrassingly parallel: symbol -> {reciprocal of freq, bias, freq, bypass
-//                             payload}.  The 64-bit division of the reference's Rans64EncPut is replaced
-//                             by Alverson reciprocal multiplication (rans64.h:167-278 shows the exact
-//                             equivalence), so no division is left on the serial path.
-//   (2) rans_encode_kernel    one warp per stream walks the records back to front.  All 32 lanes carry
-//                             the state redundantly (warp-uniform control flow); records are fetched
-//                             32 at a time with one coalesced 16-byte load per lane and handed round by
-//                             shuffles; emitted words are parked one per lane and stored 128 B at a time.
+//   (1) rans_records_kernel   embarrassingly parallel: symbol -> 32-byte record {reciprocal of freq, renorm
+//                             threshold, 2^16 - freq, shift, bias, escape payload}.  The 64-bit division of
+//                             the reference's Rans64EncPut becomes an Alverson reciprocal multiplication
+//                             (rans64.h:167-278 proves the equivalence), so no division is left on the
+//                             serial path.
+//   (2) rans_encode_kernel    one warp per stream walks the records back to front: two broadcast LDS.128 per
+//                             symbol from a double-buffered shared-memory stage, one predicated store per
+//                             emitted word into a shared buffer that is drained coalesced between chunks.
 //   (3) rans_pack_kernel      moves every stream's bytes to its final offset in one packed buffer.
-// Decoder = one kernel, one warp per stream, CDF rows (uint16, ragged) and a per-table 2^k-entry
-//   "cum >> (16-k) -> first candidate symbol" table staged in shared memory; the symbol search is a
-//   single ballot over 32 consecutive CDF entries (the reference scans linearly from entry 0).
+// Decoder = one kernel, one warp per stream.  CDF rows (32-bit entries, each row followed by 31 sentinels
+//   so that any 32-entry window is safe), a per-table 2^k-entry "cum >> (16-k) -> first candidate" table
+//   and per-table metadata live in shared memory.  The table of symbol k+1 is known in advance (indexes
+//   are an input), so a speculative window of its row (the whole row for tables with <= 32 entries, else
+//   the 32 entries around the mode) is loaded while symbol k is decoded; every lane forms
+//   freq * (x >> 16) + cum - start for its own entry and the winner's result is shuffled out.
 #include "common.cuh"
 
 #include <new>
@@ -23,15 +31,17 @@ namespace icm {
 
 constexpr int kPrecision = 16;
 constexpr uint64_t kRansL = 1ull << 31;
+constexpr uint32_t kSentinel = 0x10000u; // == cdf[last]; also pads every row in the decoder's table
+constexpr int kRowPad = 31;
 
 struct TablesDev {
-    int n_cdf, stride, lut_bits, total16;
-    const int32_t *cdf32;   // [n_cdf][stride]
-    const int32_t *sizes;   // [n_cdf]
-    const int32_t *offsets; // [n_cdf]
-    const uint16_t *cdf16;  // ragged rows, entry "size-1" (== 65536) is implied
-    const int32_t *base;    // [n_cdf] first entry of row t inside cdf16
-    const uint16_t *lut;    // [n_cdf << lut_bits]
+    int n_cdf, stride, lut_bits, total_pad;
+    const int32_t *cdf32;    // [n_cdf][stride]               (encoder gathers)
+    const int32_t *sizes;    // [n_cdf]
+    const int32_t *offsets;  // [n_cdf]
+    const uint32_t *cdf_pad; // decoder rows: size entries + 31 sentinels each
+    const int32_t *base;     // [n_cdf] first entry of row t inside cdf_pad
+    const uint16_t *lut;     // [n_cdf << lut_bits]
 };
 
 }  // namespace icm
@@ -55,43 +65,80 @@ struct icm_rans_decoder {
 
 namespace icm {
 
+// shared-memory accessors on 32-bit shared-window addresses (keeps the address arithmetic out of the loops)
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    // laundered through an opaque move so that the compiler keeps the address in a register instead of
+    // re-deriving the shared window (S2UR SR_CgaCtaId + ULEA) at every use inside the serial loops
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
-// (1) records.  One 16-byte record per symbol drives a branch-free state update
+// (1) records.  Per symbol a 32-byte record drives the branch-free state update
 //        if (hi32(x) >= thi) { emit lo32(x); x >>= 32; }          thi = freq << 15  (x_max = freq << 47)
 //        q = mulhi64(x, rcp) >> shift;  x += bias + q * cmpl;      cmpl = 2^16 - freq
-//     which equals Rans64EncPut's  x = (x / freq << 16) + x % freq + start  (rans64.h:167-278).
+//     == Rans64EncPut's  x = (x / freq << 16) + x % freq + start.  Streams are padded to a multiple of 32
+//     records with identity records (thi = ~0, everything else 0).
 struct __align__(16) Record {
-    uint32_t rcp_lo, rcp_hi; // fixed-point reciprocal of freq (rans64.h:223-241)
-    uint32_t meta;           // cmpl[0..16] | rcp_shift[17..20] | bypass[21] | nibbles[24..27]
-    uint32_t bias;           // start (freq >= 2) or start + 65535 (freq == 1)
+    uint32_t rcp_lo, rcp_hi, thi, cmpl; // first LDS.128
+    uint32_t shift, bias, escape, raw;  // second LDS.128; escape = 0 or 0x100 | nibbles
 };
-constexpr uint32_t kRecBypass = 1u << 21;
 
 __global__ void __launch_bounds__(256) rans_records_kernel(TablesDev T, const int32_t *__restrict__ sym,
-                                                           const int32_t *__restrict__ idx, long long n_total,
-                                                           long long n_per_stream, Record *__restrict__ rec,
-                                                           uint32_t *__restrict__ raw_out,
-                                                           int32_t *__restrict__ status)
+                                                           const int32_t *__restrict__ idx, int n_streams,
+                                                           long long n_per_stream, long long n_pad,
+                                                           Record *__restrict__ rec, int32_t *__restrict__ status)
 {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int t = idx[i];
+    const long long total = (long long)n_streams * n_pad;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const long long s = g / n_pad, i = g - s * n_pad;
+        Record r;
+        if (i >= n_per_stream) { // identity
+            r.rcp_lo = r.rcp_hi = 0; r.thi = 0xFFFFFFFFu; r.cmpl = 0; r.shift = 0; r.bias = 0; r.escape = 0; r.raw = 0;
+            rec[g] = r;
+            continue;
+        }
+        int t = idx[s * n_per_stream + i];
         if (t < 0 || t >= T.n_cdf) { // the reference has only a compiled-out assert here (UB)
-            status[i / n_per_stream] = ICM_ERR_BAD_INDEX;
+            status[s] = ICM_ERR_BAD_INDEX;
             t = 0;
         }
         const int32_t *cdf = T.cdf32 + (size_t)t * T.stride;
         const int max_value = T.sizes[t] - 2;
-        int v = sym[i] - T.offsets[t];
+        int v = sym[s * n_per_stream + i] - T.offsets[t];
         uint32_t raw = 0;
         if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = max_value; }
         else if (v >= max_value) { raw = (uint32_t)(2 * (v - max_value)); v = max_value; }
         const uint32_t start = (uint16_t)cdf[v];
         const uint32_t freq = (uint16_t)(cdf[v + 1] - cdf[v]);
-        Record r;
-        uint32_t shift_m1 = 0;
         if (freq < 2) { // rans64.h:192-221
             r.rcp_lo = 0xFFFFFFFFu; r.rcp_hi = 0xFFFFFFFFu;
+            r.shift = 0;
             r.bias = start + (1u << kPrecision) - 1;
         } else {
             const uint32_t shift = 32 - __clz(freq - 1); // ceil(log2(freq))
@@ -101,130 +148,113 @@ __global__ void __launch_bounds__(256) rans_records_kernel(TablesDev T, const in
             const uint64_t t0 = x0 / freq;
             const uint64_t rcp = t0 + (t1 << 32);
             r.rcp_lo = (uint32_t)rcp; r.rcp_hi = (uint32_t)(rcp >> 32);
-            shift_m1 = shift - 1;
+            r.shift = shift - 1;
             r.bias = start;
         }
-        r.meta = ((1u << kPrecision) - freq) | (shift_m1 << 17);
+        r.thi = freq << 15;
+        r.cmpl = (1u << kPrecision) - freq;
+        r.escape = 0;
         if (v == max_value) {
             uint32_t nb = 0;
             while (nb < 8 && (raw >> (nb * 4)) != 0) ++nb;
-            r.meta |= kRecBypass | (nb << 24);
+            r.escape = 0x100u | nb;
         }
-        rec[i] = r;
-        raw_out[i] = raw;
+        r.raw = raw;
+        rec[g] = r;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// (2) serial walk, one warp per stream.  Every lane carries the state (warp-uniform control flow); the
-// records of 32 symbols are staged in shared memory (double buffered, next chunk's global loads in flight)
-// and read back with one broadcast LDS.128 per symbol, issued one symbol ahead of its use.  Emitted words
-// go to a 128-word shared ring (one predicated store, no branch) that is drained 128 B at a time between
-// chunks; a symbol emits at most two words (<= 52 bits of payload), so a chunk emits at most 65.
-constexpr int kRing = 128;
+// (2) serial walk, one warp per stream.  All lanes carry the state (warp-uniform control flow).
+constexpr int kEncOutWords = 96; // a 32-symbol chunk emits at most 64 words (<= 52 payload bits per symbol)
 
-struct Emitter {
-    uint32_t *ring;
-    uint32_t count, flushed; // words emitted / words already stored to global (warp-uniform)
-    uint32_t *top;           // one past the last word of the stream's scratch area
-    uint32_t capacity, overflow, lane;
-    __device__ __forceinline__ void put_if(bool emit, uint32_t w)
-    {
-        if (emit) ring[count & (kRing - 1)] = w; // every lane stores the same word: uniform, one transaction
-        count += emit ? 1u : 0u;
-    }
-    __device__ __forceinline__ void drain(bool all)
-    {
-        __syncwarp();
-        while (count - flushed >= 32u || (all && count != flushed)) {
-            const uint32_t e = flushed + lane;
-            if (e < count) {
-                if (e < capacity) *(top - 1 - e) = ring[e & (kRing - 1)]; // descending addresses, 128 B per pass
-                else overflow = 1;
-            }
-            flushed = min(flushed + 32u, count);
-        }
-        __syncwarp();
-    }
+struct EncState {
+    uint64_t x;
+    uint32_t out; // shared address of the next free word of the chunk's output buffer
 };
 
-__device__ __forceinline__ void put_bits4(uint64_t &x, uint32_t val, Emitter &e)
-{ // Rans64EncPutBits with nbits = 4: freq = 2^12, x_max = 2^59
-    const bool emit = (uint32_t)(x >> 32) >= (1u << 27);
-    e.put_if(emit, (uint32_t)x);
-    x = emit ? (x >> 32) : x;
-    x = (x << 4) | val;
+__device__ __forceinline__ void enc_put_bits4(EncState &st, uint32_t val)
+{ // Rans64EncPutBits, nbits = 4: freq = 2^12, x_max = 2^59
+    const bool emit = (uint32_t)(st.x >> 32) >= (1u << 27);
+    if (emit) { sts32(st.out, (uint32_t)st.x); st.out += 4; st.x >>= 32; }
+    st.x = (st.x << 4) | val;
 }
 
-__global__ void __launch_bounds__(32) rans_encode_kernel(const Record *__restrict__ rec,
-                                                         const uint32_t *__restrict__ raw_in,
-                                                         long long n_per_stream, uint32_t *__restrict__ words,
-                                                         long long cap_words, int32_t *__restrict__ sizes,
-                                                         const int32_t *__restrict__ status)
+// records of an escaped symbol, in push order: main, count(nb), nibble_0..nibble_{nb-1}; drained back to
+// front.  nb <= 8 < 15, so the count is a single nibble.  Out of line: rare on real data.
+__device__ __noinline__ EncState enc_escape(EncState st, uint32_t raw, uint32_t nb)
 {
-    __shared__ uint4 s_rec[2][32];
-    __shared__ uint32_t s_raw[2][32];
-    __shared__ uint32_t s_ring[kRing];
-    const int s = blockIdx.x, lane = threadIdx.x;
-    const uint4 *R = reinterpret_cast<const uint4 *>(rec + (size_t)s * n_per_stream);
-    const uint32_t *RAW = raw_in + (size_t)s * n_per_stream;
-    Emitter e;
-    e.ring = s_ring; e.count = 0; e.flushed = 0; e.lane = lane; e.overflow = 0;
-    e.top = words + (size_t)(s + 1) * cap_words;
-    e.capacity = (uint32_t)cap_words;
-    uint64_t x = kRansL;
+    for (int j = (int)nb - 1; j >= 0; --j) enc_put_bits4(st, (raw >> (j * 4)) & 15u);
+    enc_put_bits4(st, nb);
+    return st;
+}
 
-    const long long n_chunks = (n_per_stream + 31) / 32;
-    uint4 g = make_uint4(0, 0, 0, 0);
-    uint32_t graw = 0;
+__global__ void __launch_bounds__(32) rans_encode_kernel(const Record *__restrict__ rec, long long n_pad,
+                                                         uint32_t *__restrict__ words, long long cap_words,
+                                                         int32_t *__restrict__ sizes, const int32_t *__restrict__ status)
+{
+    __shared__ __align__(16) uint4 s_rec[2][64]; // [buffer][symbol * 2 + half]
+    __shared__ uint32_t s_out[kEncOutWords];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const uint4 *R = reinterpret_cast<const uint4 *>(rec + (size_t)s * n_pad);
+    uint32_t *top = words + (size_t)(s + 1) * cap_words; // one past the last word of this stream's scratch
+    const uint32_t rec_base = smem_addr(&s_rec[0][0]), out_base = smem_addr(&s_out[0]);
+    EncState st;
+    st.x = kRansL;
+    st.out = out_base;
+    uint32_t total = 0; // words stored to global so far
+    bool overflow = false;
+    auto drain = [&]() {
+        __syncwarp();
+        const uint32_t n = (st.out - out_base) >> 2;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t e = total + i;
+            if (e < (uint32_t)cap_words) *(top - 1 - e) = s_out[i]; // descending addresses
+            else overflow = true;
+        }
+        total += n;
+        st.out = out_base;
+        __syncwarp();
+    };
+
+    const long long n_chunks = n_pad / 32;
+    uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
     if (n_chunks > 0) {
-        const long long j = (n_chunks - 1) * 32 + lane;
-        if (j < n_per_stream) { g = __ldg(R + j); graw = __ldg(RAW + j); }
+        const long long j = ((n_chunks - 1) * 32 + lane) * 2;
+        g0 = __ldg(R + j); g1 = __ldg(R + j + 1);
     }
     for (long long c = n_chunks - 1; c >= 0; --c) {
-        const int buf = (int)(c & 1);
-        s_rec[buf][lane] = g;
-        s_raw[buf][lane] = graw;
+        const uint32_t buf = rec_base + (uint32_t)(c & 1) * 1024u;
+        sts128(buf + lane * 32, g0);
+        sts128(buf + lane * 32 + 16, g1);
         if (c > 0) { // the next (earlier) chunk's loads fly while this one is coded
-            const long long j = (c - 1) * 32 + lane;
-            g = __ldg(R + j);
-            graw = __ldg(RAW + j);
+            const long long j = ((c - 1) * 32 + lane) * 2;
+            g0 = __ldg(R + j); g1 = __ldg(R + j + 1);
         }
-        e.drain(false); // also orders the staging stores above before the reads below
-        const int valid = (int)min(32LL, n_per_stream - c * 32);
-        uint4 cur = s_rec[buf][valid - 1];
-#pragma unroll 1
-        for (int k = valid - 1; k >= 0; --k) {
-            const uint4 nxt = s_rec[buf][k > 0 ? k - 1 : 0];
-            if (cur.z & kRecBypass) {
-                // records of an escaped symbol, in push order: main, count(nb), nibble_0..nibble_{nb-1};
-                // drained back to front.  nb <= 8 < 15, so the count is a single nibble.
-                const uint32_t raw = s_raw[buf][k];
-                const int nb = (int)((cur.z >> 24) & 15u);
-#pragma unroll 1
-                for (int j = nb - 1; j >= 0; --j) put_bits4(x, (raw >> (j * 4)) & 15u, e);
-                put_bits4(x, (uint32_t)nb, e);
-            }
-            const uint32_t cmpl = cur.z & 0x1FFFFu;
-            const uint32_t shift = (cur.z >> 17) & 15u;
-            const uint32_t thi = ((1u << kPrecision) - cmpl) << 15;
-            const bool emit = (uint32_t)(x >> 32) >= thi;
-            e.put_if(emit, (uint32_t)x);
-            x = emit ? (x >> 32) : x;
-            const uint64_t rcp = ((uint64_t)cur.y << 32) | cur.x;
-            const uint64_t q = __umul64hi(x, rcp) >> shift;
-            x = x + cur.w + q * (uint64_t)cmpl;
-            cur = nxt;
+        drain(); // also orders the staging stores above before the reads below
+        uint4 a = lds128(buf + 31 * 32), b = lds128(buf + 31 * 32 + 16);
+#pragma unroll 8
+        for (int k = 31; k >= 0; --k) {
+            const uint32_t nk = (uint32_t)(k > 0 ? k - 1 : 0) * 32;
+            const uint4 na = lds128(buf + nk), nb = lds128(buf + nk + 16); // next record, ahead of its use
+            if (b.z) st = enc_escape(st, b.w, b.z & 15u);
+            const bool emit = (uint32_t)(st.x >> 32) >= a.z;
+            if (emit) { sts32(st.out, (uint32_t)st.x); st.out += 4; st.x >>= 32; }
+            const uint64_t rcp = ((uint64_t)a.y << 32) | a.x;
+            const uint64_t q = __umul64hi(st.x, rcp) >> b.x;
+            st.x = st.x + b.y + q * (uint64_t)a.w;
+            a = na; b = nb;
         }
     }
     // Rans64EncFlush: ptr -= 2; ptr[0] = lo; ptr[1] = hi  => hi is the "earlier" emitted word
-    e.drain(false);
-    e.put_if(true, (uint32_t)(x >> 32));
-    e.put_if(true, (uint32_t)x);
-    e.drain(true);
+    sts32(st.out, (uint32_t)(st.x >> 32));
+    sts32(st.out + 4, (uint32_t)st.x);
+    st.out += 8;
+    drain();
+    overflow = __any_sync(0xffffffffu, overflow);
     if (lane == 0) {
-        const int32_t st = status[s];
-        sizes[s] = st < 0 ? st : (e.overflow ? ICM_ERR_CAPACITY : (int32_t)(e.count * 4));
+        const int32_t stat = status[s];
+        sizes[s] = stat < 0 ? stat : (overflow ? ICM_ERR_CAPACITY : (int32_t)(total * 4));
     }
 }
 
@@ -288,18 +318,95 @@ __global__ void __launch_bounds__(256) rans_pack_kernel(const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// decoder: one warp per stream.  Per-symbol critical path (all lanes carry x):
-//     cum = x & 0xFFFF -> 32 lanes compare one CDF entry each -> ballot -> ffs -> every lane has already
-//     formed freq * (x >> 16) + cum - start for ITS entry; the winner's 64-bit result is shuffled out -> renorm.
-// Everything else is taken off that path: the table of symbol k+1 is known in advance (indexes are an
-// input), so its metadata and a speculative 32-entry window of its CDF row (the whole row for tables with
-// <= 32 entries, else the 32 entries around the distribution's centre) are loaded from shared memory while
-// symbol k is decoded.  Only when cum falls outside that window does the coder take the general route:
-// the per-table "cum >> (16-k) -> first candidate" table, then 32-entry windows until one brackets cum.
-__device__ __forceinline__ uint32_t cdf_window(const uint16_t *s_cdf, uint32_t base, int size, int s0, int lane)
+// decoder
+struct DecState {
+    uint32_t xl, xh;      // rANS state
+    uint32_t pos;         // next stream word
+    uint32_t wcur, wnxt;  // lane l: words (pos & ~31) + l and + 32 + l
+    uint32_t wv;          // the next stream word, broadcast, always ready
+};
+
+struct DecCtx {
+    const uint32_t *W;
+    uint32_t nwords;
+    int lane;
+};
+
+__device__ __forceinline__ uint32_t dec_load_block(const DecCtx &c, uint32_t block)
 {
-    const int cand = s0 + lane;
-    return (cand >= size - 1) ? 0x10000u : (uint32_t)s_cdf[base + cand]; // entry size-1 is 65536 by definition
+    const uint32_t j = block * 32 + c.lane;
+    return j < c.nwords ? __ldg(c.W + j) : 0u; // past-the-end reads are UB in the reference; we feed zeros
+}
+
+// called after pos was incremented
+__device__ __forceinline__ void dec_after_consume(DecState &d, const DecCtx &c)
+{
+    if ((d.pos & 31u) == 0) { d.wcur = d.wnxt; d.wnxt = dec_load_block(c, (d.pos >> 5) + 1); }
+    d.wv = __shfl_sync(0xffffffffu, d.wcur, (int)(d.pos & 31u));
+}
+
+__device__ __forceinline__ uint32_t dec_get4(DecState &d, const DecCtx &c)
+{ // Rans64DecGetBits, n_bits = 4
+    const uint32_t val = d.xl & 15u;
+    d.xl = (d.xl >> 4) | (d.xh << 28);
+    d.xh >>= 4;
+    if (d.xh == 0 && d.xl < 0x80000000u) { d.xh = d.xl; d.xl = d.wv; ++d.pos; dec_after_consume(d, c); }
+    return val;
+}
+
+// everything that is not the common path: cum outside the speculative window, an escape symbol, or the
+// 32-word stream window running out.  Returns the decoded value.
+struct SlowArgs {
+    uint32_t cum, xs_lo, xs_hi; // from the state before the symbol
+    uint32_t p;                 // entries <= cum inside the speculative window
+    uint32_t row_addr, size, s0, lut_addr, lut_shift;
+    int offset;
+};
+
+struct SlowRet {
+    DecState d;
+    int value;
+};
+
+// by value in, by value out: keeps the caller's state in registers (a reference would pin it to local memory)
+__device__ __noinline__ SlowRet dec_slow(DecState d, DecCtx c, SlowArgs a, uint32_t nxl, uint32_t nxh)
+{
+    uint32_t s0 = a.s0, p = a.p;
+    if (p - 1u >= 31u) { // general search: per-table bucket table, then windows until one brackets cum
+        s0 = lds16(a.lut_addr + ((a.cum >> a.lut_shift) << 1));
+        uint32_t e, m;
+        while (true) {
+            e = lds32(a.row_addr + ((s0 + c.lane) << 2));
+            m = __ballot_sync(0xffffffffu, e <= a.cum);
+            if (m != 0xffffffffu) break;
+            s0 += 31; // more than 31 symbols share this bucket
+        }
+        p = __popc(m); // >= 1: entry s0 is <= cum by construction of the bucket table
+        const uint32_t start = __shfl_sync(0xffffffffu, e, (int)p - 1);
+        const uint32_t next = __shfl_sync(0xffffffffu, e, (int)p);
+        const uint32_t f = next - start;
+        const uint64_t nx = (uint64_t)f * a.xs_lo + (a.cum - start) + ((uint64_t)(f * a.xs_hi) << 32);
+        nxl = (uint32_t)nx; nxh = (uint32_t)(nx >> 32);
+    }
+    // Rans64DecAdvance tail
+    d.xl = nxl; d.xh = nxh;
+    if (d.xh == 0 && d.xl < 0x80000000u) { d.xh = d.xl; d.xl = d.wv; ++d.pos; dec_after_consume(d, c); }
+    const int symbol = (int)(s0 + p) - 1;
+    const int max_value = (int)a.size - 2;
+    int value = symbol;
+    if (symbol == max_value) { // escape: count nibble(s), then the payload nibbles, LSB first
+        int val = (int)dec_get4(d, c);
+        int nb = val;
+        while (val == 15) { val = (int)dec_get4(d, c); nb += val; }
+        int raw = 0;
+        for (int j = 0; j < nb; ++j) { val = (int)dec_get4(d, c); raw |= val << ((j * 4) & 31); }
+        value = raw >> 1;
+        if (raw & 1) value = -value - 1; else value += max_value;
+    }
+    SlowRet r;
+    r.d = d;
+    r.value = value + a.offset;
+    return r;
 }
 
 __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint32_t *__restrict__ words,
@@ -310,151 +417,135 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint
                                                          int32_t *__restrict__ out, int32_t *__restrict__ status)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t *s_cdf = reinterpret_cast<uint16_t *>(smem_raw);
-    uint16_t *s_lut = s_cdf + ((T.total16 + 7) & ~7);
-    uint4 *s_meta = reinterpret_cast<uint4 *>(s_lut + ((size_t)T.n_cdf << T.lut_bits)); // {base, size | t << 16, offset, s0}
-    __shared__ uint4 s_sym[2][32];
+    uint32_t *s_cdf = reinterpret_cast<uint32_t *>(smem_raw);
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_cdf + ((T.total_pad + 3) & ~3));
+    uint4 *s_meta = reinterpret_cast<uint4 *>(s_lut + ((size_t)T.n_cdf << T.lut_bits)); // per table
+    __shared__ __align__(16) uint4 s_sym[64]; // per symbol: two chunks of 32
+    __shared__ int32_t s_val[32];
     const int lane = threadIdx.x;
+    const uint32_t cdf_addr = smem_addr(s_cdf), lut_addr = smem_addr(s_lut), sym_addr = smem_addr(s_sym), val_addr = smem_addr(s_val);
     {
-        const uint4 *g = reinterpret_cast<const uint4 *>(T.cdf16);
+        const uint4 *g = reinterpret_cast<const uint4 *>(T.cdf_pad);
         uint4 *d = reinterpret_cast<uint4 *>(s_cdf);
-        for (int i = lane; i < (T.total16 + 7) / 8; i += 32) d[i] = g[i];
+        for (int i = lane; i < (T.total_pad + 3) / 4; i += 32) d[i] = __ldg(g + i);
         const uint4 *gl = reinterpret_cast<const uint4 *>(T.lut);
         uint4 *dl = reinterpret_cast<uint4 *>(s_lut);
-        for (int i = lane; i < (int)(((size_t)T.n_cdf << T.lut_bits) / 8); i += 32) dl[i] = gl[i];
+        for (int i = lane; i < (int)(((size_t)T.n_cdf << T.lut_bits) / 8); i += 32) dl[i] = __ldg(gl + i);
         for (int i = lane; i < T.n_cdf; i += 32) {
-            const int size = T.sizes[i], off = T.offsets[i];
+            // per table: {speculative window address, s0 + offset - 1, size - 1 - s0 (the p that means "escape"), t | s0 << 16}
+            const int size = T.sizes[i], off = T.offsets[i], base = T.base[i];
             int s0 = 0;
             if (size > 32) { s0 = -off - 15; s0 = max(0, min(s0, size - 32)); }
-            s_meta[i] = make_uint4((uint32_t)T.base[i], (uint32_t)size | ((uint32_t)i << 16), (uint32_t)off, (uint32_t)s0);
+            s_meta[i] = make_uint4(cdf_addr + (uint32_t)(base + s0) * 4u, (uint32_t)(s0 + off - 1), (uint32_t)(size - 1 - s0),
+                                   (uint32_t)i | ((uint32_t)s0 << 16));
         }
     }
     __syncwarp();
 
     const int s = blockIdx.x;
-    const uint32_t *W = words + word_off[s];
-    const long long nwords = nwords_arr[s];
-    uint64_t x;
-    long long pos = pos_arr[s];
-    if (pos < 0) { // set_stream: Rans64DecInit
-        const uint32_t w0 = nwords > 0 ? W[0] : 0u, w1 = nwords > 1 ? W[1] : 0u;
-        x = (uint64_t)w0 | ((uint64_t)w1 << 32);
-        pos = 2;
-    } else {
-        x = state[s];
+    DecCtx ctx;
+    ctx.W = words + word_off[s];
+    ctx.nwords = (uint32_t)min((long long)nwords_arr[s], 0xFFFFFFFFLL);
+    ctx.lane = lane;
+    DecState d;
+    {
+        const long long pos0 = pos_arr[s];
+        if (pos0 < 0) { // set_stream: Rans64DecInit
+            d.xl = ctx.nwords > 0 ? ctx.W[0] : 0u;
+            d.xh = ctx.nwords > 1 ? ctx.W[1] : 0u;
+            d.pos = 2;
+        } else {
+            const uint64_t x = state[s];
+            d.xl = (uint32_t)x; d.xh = (uint32_t)(x >> 32);
+            d.pos = (uint32_t)pos0;
+        }
     }
-    // word window: lane l of wcur holds word (wblock*32 + l); wnxt is the following block
-    long long wblock = pos >> 5;
-    auto load_block = [&](long long b) -> uint32_t {
-        const long long j = b * 32 + lane;
-        return j < nwords ? __ldg(W + j) : 0u; // past-the-end reads are UB in the reference; we feed zeros
-    };
-    uint32_t wcur = load_block(wblock), wnxt = load_block(wblock + 1);
-    uint32_t wv = __shfl_sync(0xffffffffu, wcur, (int)(pos & 31)); // the next stream word, always kept ready
-    // renormalise (Rans64DecAdvance tail / Rans64DecGetBits tail): predicated, plus a rare window refill
-    auto renorm = [&]() {
-        const bool rn = x < kRansL;
-        x = rn ? ((x << 32) | wv) : x;
-        pos += rn ? 1 : 0;
-        if (rn && (pos & 31) == 0) { wcur = wnxt; ++wblock; wnxt = load_block(wblock + 1); }
-        wv = __shfl_sync(0xffffffffu, wcur, (int)(pos & 31));
-    };
-    auto get4 = [&]() -> int {
-        const int val = (int)(x & 15u);
-        x >>= 4;
-        renorm();
-        return val;
-    };
+    d.wcur = dec_load_block(ctx, d.pos >> 5);
+    d.wnxt = dec_load_block(ctx, (d.pos >> 5) + 1);
+    d.wv = __shfl_sync(0xffffffffu, d.wcur, (int)(d.pos & 31u));
 
     const int32_t *I = idx + (size_t)s * n_per_stream;
     int32_t *O = out + (size_t)s * n_per_stream;
-    const int lut_shift = kPrecision - T.lut_bits;
+    const uint32_t lut_shift = kPrecision - T.lut_bits;
     const long long n = n_per_stream;
     const long long n_chunks = (n + 31) / 32;
+    const uint32_t lane4 = lane * 4;
     bool bad = false;
-    auto meta_of = [&](int t) -> uint4 {
+    auto stage = [&](long long c, int t) { // per-symbol metadata of chunk c into its half of s_sym
         if (t < 0 || t >= T.n_cdf) { bad = true; t = 0; }
-        return s_meta[t];
-    };
-    auto sym_at = [&](long long g) -> uint4 {
-        g = min(g, n - 1);
-        return s_sym[(g >> 5) & 1][g & 31];
+        s_sym[(c & 1) * 32 + lane] = s_meta[t];
     };
     int ireg = (lane < n) ? __ldg(I + lane) : 0;
-    s_sym[0][lane] = meta_of(ireg);
+    s_sym[32 + lane] = s_meta[0]; // the look-ahead past the last symbol must still read a valid window address
+    stage(0, ireg);
     ireg = (32 + lane < n) ? __ldg(I + 32 + lane) : 0;
     __syncwarp();
-    uint4 meta0 = sym_at(0), meta1 = sym_at(1);
-    uint32_t v0 = cdf_window(s_cdf, meta0.x, (int)(meta0.y & 0xFFFFu), (int)meta0.w, lane);
-    uint32_t f0 = __shfl_down_sync(0xffffffffu, v0, 1) - v0;
+    // operands of the first symbol
+    uint4 mc = lds128(sym_addr);
+    uint32_t e = lds32(mc.x + lane4);
+    uint32_t eprev = __shfl_up_sync(0xffffffffu, e, 1);
+    uint32_t f = e - eprev;
 
     for (long long c = 0; c < n_chunks; ++c) {
         __syncwarp();
-        if (c + 1 < n_chunks) { // stage the next chunk's per-symbol metadata; its indexes were fetched a chunk ago
-            s_sym[(c + 1) & 1][lane] = meta_of(ireg);
+        if (c + 1 < n_chunks) { // stage the next chunk; its indexes were fetched one chunk ago
+            stage(c + 1, ireg);
             const long long j = (c + 2) * 32 + lane;
             ireg = (j < n) ? __ldg(I + j) : 0;
         }
         __syncwarp();
         const int valid = (int)min(32LL, n - c * 32);
-        int result = 0;
-#pragma unroll 1
+        const uint32_t sym_chunk = (uint32_t)(c & 1) * 512u;
+#pragma unroll 2
         for (int k = 0; k < valid; ++k) {
-            const long long gk = c * 32 + k;
-            // ---- off the critical path: operands of the next two symbols, the next stream word
-            const uint32_t v1 = cdf_window(s_cdf, meta1.x, (int)(meta1.y & 0xFFFFu), (int)meta1.w, lane);
-            const uint4 meta2 = sym_at(gk + 2);
-            const int size = (int)(meta0.y & 0xFFFFu);
+            // ---- off the critical path: metadata of symbol k+1 (its half of s_sym was staged a chunk ago)
+            const uint4 mn = lds128(sym_addr + ((sym_chunk + (uint32_t)(k + 1) * 16u) & 1023u));
             // ---- critical path
-            const uint32_t cum = (uint32_t)x & 0xFFFFu;
-            uint32_t vv = v0, ff = f0;
-            int s0 = (int)meta0.w;
-            uint32_t m = __ballot_sync(0xffffffffu, vv > cum);
-            if ((m & 1u) | (m == 0u)) { // cum is outside the speculative window
-                const int t = (int)(meta0.y >> 16);
-                s0 = s_lut[(t << T.lut_bits) + (cum >> lut_shift)];
-                while (true) {
-                    vv = cdf_window(s_cdf, meta0.x, size, s0, lane);
-                    m = __ballot_sync(0xffffffffu, vv > cum);
-                    if (m != 0u) break;
-                    s0 += 31; // more than 31 symbols share this bucket
-                }
-                ff = __shfl_down_sync(0xffffffffu, vv, 1) - vv;
+            const uint32_t cum = d.xl & 0xFFFFu;
+            const uint32_t p = __popc(__ballot_sync(0xffffffffu, e <= cum)); // entries <= cum: a prefix of the lanes
+            const uint32_t xs_lo = (d.xl >> 16) | (d.xh << 16), xs_hi = d.xh >> 16;
+            // Rans64DecAdvance formed by every lane for the symbol that ENDS at its entry; lane p holds the real one
+            const uint64_t nx = (uint64_t)f * xs_lo + (uint64_t)(cum - eprev) + ((uint64_t)(f * xs_hi) << 32);
+            const uint32_t nxl = __shfl_sync(0xffffffffu, (uint32_t)nx, (int)p);
+            const uint32_t nxh = __shfl_sync(0xffffffffu, (uint32_t)(nx >> 32), (int)p);
+            const uint32_t en = lds32(mn.x + lane4); // speculative window of symbol k+1
+            const bool rn = (nxh == 0) && (nxl < 0x80000000u);
+            const uint32_t npos = d.pos + (rn ? 1u : 0u);
+            int value = (int)(mc.y + p);
+            const bool slow = (p - 1u >= 31u) | (p == mc.z) | (rn & ((npos & 31u) == 0));
+            if (!slow) {
+                d.xl = rn ? d.wv : nxl;
+                d.xh = rn ? nxl : nxh;
+                d.pos = npos;
+                d.wv = __shfl_sync(0xffffffffu, d.wcur, (int)(npos & 31u));
+            } else {
+                SlowArgs a;
+                a.cum = cum; a.xs_lo = xs_lo; a.xs_hi = xs_hi; a.p = p;
+                const uint32_t t = mc.w & 0xFFFFu;
+                a.s0 = mc.w >> 16;
+                a.row_addr = mc.x - a.s0 * 4u;
+                a.size = mc.z + 1u + a.s0;
+                a.lut_addr = lut_addr + ((t << T.lut_bits) << 1);
+                a.lut_shift = lut_shift;
+                a.offset = (int)mc.y + 1 - (int)a.s0;
+                const SlowRet r = dec_slow(d, ctx, a, nxl, nxh);
+                d = r.d;
+                value = r.value;
             }
-            const int p = __ffs(m) - 1; // >= 1: entry s0 is <= cum
-            // Rans64DecAdvance, formed by every lane for its own entry; lane p-1 holds the real one
-            const uint64_t nx = (uint64_t)ff * (x >> kPrecision) + (uint64_t)(cum - vv);
-            const uint32_t nlo = __shfl_sync(0xffffffffu, (uint32_t)nx, p - 1);
-            const uint32_t nhi = __shfl_sync(0xffffffffu, (uint32_t)(nx >> 32), p - 1);
-            x = ((uint64_t)nhi << 32) | nlo;
-            renorm();
-            const int symbol = s0 + p - 1;
-            int value = symbol;
-            if (symbol == size - 2) { // bypass escape
-                const int max_value = size - 2;
-                int val = get4();
-                int nb = val;
-#pragma unroll 1
-                while (val == 15) { val = get4(); nb += val; }
-                int raw = 0;
-#pragma unroll 1
-                for (int j = 0; j < nb; ++j) { val = get4(); raw |= val << ((j * 4) & 31); }
-                value = raw >> 1;
-                if (raw & 1) value = -value - 1; else value += max_value;
-            }
-            value += (int)meta0.z;
-            if (lane == k) result = value;
-            // ---- rotate the pipeline
-            meta0 = meta1; meta1 = meta2;
-            v0 = v1;
-            f0 = __shfl_down_sync(0xffffffffu, v1, 1) - v1;
+            sts32(val_addr + (uint32_t)k * 4u, (uint32_t)value);
+            // ---- operands of the next symbol
+            mc = mn;
+            e = en;
+            eprev = __shfl_up_sync(0xffffffffu, en, 1);
+            f = en - eprev;
         }
-        if (lane < valid) O[c * 32 + lane] = result;
+        __syncwarp();
+        if (lane < valid) O[c * 32 + lane] = s_val[lane];
     }
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
-        state[s] = x;
-        pos_arr[s] = pos;
+        state[s] = ((uint64_t)d.xh << 32) | d.xl;
+        pos_arr[s] = (int64_t)d.pos;
         if (bad) status[s] = ICM_ERR_BAD_INDEX;
     }
 }
@@ -469,31 +560,32 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
                                  const int32_t *h_offsets, icm_tables **out)
 {
     ICM_CHECK_ARG(h_cdfs && h_sizes && h_offsets && out, "icm_tables_create: null argument");
-    ICM_CHECK_ARG(n_cdf > 0 && stride >= 3, "icm_tables_create: bad shape n_cdf=%d stride=%d", n_cdf, stride);
+    ICM_CHECK_ARG(n_cdf > 0 && n_cdf < 65536 && stride >= 3, "icm_tables_create: bad shape n_cdf=%d stride=%d", n_cdf, stride);
     std::vector<int32_t> base(n_cdf);
     int total = 0;
     for (int t = 0; t < n_cdf; ++t) {
         const int size = h_sizes[t];
-        ICM_CHECK_ARG(size >= 3 && size <= stride, "icm_tables_create: cdf_size[%d]=%d outside [3,%d]", t, size, stride);
+        ICM_CHECK_ARG(size >= 3 && size <= stride && size < 65536, "icm_tables_create: cdf_size[%d]=%d outside [3,%d]", t, size, stride);
         const int32_t *c = h_cdfs + (size_t)t * stride;
         ICM_CHECK_ARG(c[0] == 0 && c[size - 1] == (1 << kPrecision), "icm_tables_create: row %d is not a 16-bit CDF", t);
         for (int j = 0; j + 1 < size; ++j)
             ICM_CHECK_ARG(c[j] < c[j + 1], "icm_tables_create: row %d not strictly increasing at %d", t, j);
         base[t] = total;
-        total += (size + 1) & ~1; // keep rows 4-byte aligned
+        total += size + kRowPad;
     }
     int lut_bits = 8;
     auto smem_need = [&](int bits) {
-        return (size_t)((total + 7) & ~7) * 2 + ((size_t)n_cdf << bits) * 2 + (size_t)n_cdf * 16;
+        return (size_t)((total + 3) & ~3) * 4 + ((size_t)n_cdf << bits) * 2 + (size_t)n_cdf * 16;
     };
-    while (lut_bits > 3 && smem_need(lut_bits) > 200 * 1024) --lut_bits;
-    ICM_CHECK_ARG(smem_need(lut_bits) <= 200 * 1024, "icm_tables_create: tables too large for shared memory");
+    while (lut_bits > 3 && smem_need(lut_bits) > 220 * 1024) --lut_bits;
+    ICM_CHECK_ARG(smem_need(lut_bits) <= 220 * 1024, "icm_tables_create: tables too large for shared memory");
     const size_t lut_n = (size_t)n_cdf << lut_bits;
-    std::vector<uint16_t> cdf16(((size_t)total + 7) & ~(size_t)7, 0), lut(lut_n);
+    std::vector<uint32_t> cdf_pad(((size_t)total + 3) & ~(size_t)3, kSentinel);
+    std::vector<uint16_t> lut(lut_n);
     for (int t = 0; t < n_cdf; ++t) {
         const int size = h_sizes[t];
         const int32_t *c = h_cdfs + (size_t)t * stride;
-        for (int j = 0; j < size; ++j) cdf16[base[t] + j] = (uint16_t)c[j]; // 65536 wraps to 0; implied by position
+        for (int j = 0; j < size; ++j) cdf_pad[base[t] + j] = (uint32_t)c[j];
         int sidx = 0;
         for (int b = 0; b < (1 << lut_bits); ++b) {
             const int32_t lo = b << (kPrecision - lut_bits);
@@ -501,17 +593,17 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
             lut[((size_t)t << lut_bits) + b] = (uint16_t)sidx;
         }
     }
-    // one device blob: cdf32 | sizes | offsets | base | cdf16 | lut
+    // one device blob: cdf32 | sizes | offsets | base | cdf_pad | lut
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_cdf32 = 0, o_sizes = al(o_cdf32 + (size_t)n_cdf * stride * 4), o_offsets = al(o_sizes + n_cdf * 4),
-                 o_base = al(o_offsets + n_cdf * 4), o_cdf16 = al(o_base + n_cdf * 4),
-                 o_lut = al(o_cdf16 + cdf16.size() * 2), blob_bytes = al(o_lut + lut_n * 2);
+                 o_base = al(o_offsets + n_cdf * 4), o_pad = al(o_base + n_cdf * 4),
+                 o_lut = al(o_pad + cdf_pad.size() * 4), blob_bytes = al(o_lut + lut_n * 2);
     std::vector<unsigned char> host(blob_bytes, 0);
     memcpy(&host[o_cdf32], h_cdfs, (size_t)n_cdf * stride * 4);
     memcpy(&host[o_sizes], h_sizes, n_cdf * 4);
     memcpy(&host[o_offsets], h_offsets, n_cdf * 4);
     memcpy(&host[o_base], base.data(), n_cdf * 4);
-    memcpy(&host[o_cdf16], cdf16.data(), cdf16.size() * 2);
+    memcpy(&host[o_pad], cdf_pad.data(), cdf_pad.size() * 4);
     memcpy(&host[o_lut], lut.data(), lut_n * 2);
     icm_tables *T = new (std::nothrow) icm_tables();
     ICM_CHECK_ARG(T, "icm_tables_create: out of host memory");
@@ -522,7 +614,7 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
     char *b = (char *)T->d_blob;
     T->dev = TablesDev{n_cdf, stride, lut_bits, total,
                        (const int32_t *)(b + o_cdf32), (const int32_t *)(b + o_sizes), (const int32_t *)(b + o_offsets),
-                       (const uint16_t *)(b + o_cdf16), (const int32_t *)(b + o_base), (const uint16_t *)(b + o_lut)};
+                       (const uint32_t *)(b + o_pad), (const int32_t *)(b + o_base), (const uint16_t *)(b + o_lut)};
     T->smem_bytes = smem_need(lut_bits);
     *out = T;
     return ICM_OK;
@@ -537,21 +629,20 @@ extern "C" void icm_tables_destroy(icm_tables *t)
 
 static inline long long enc_cap_words(long long n)
 {
-    // worst case per symbol: 16 bits + escape (unary nibble + 8 payload nibbles) = 52 bits; + final state
+    // worst case per symbol: 16 bits + escape (count nibble + 8 payload nibbles) = 52 bits; + final state
     long long w = (n * 52 + 31) / 32 + 2;
     return (w + 31) & ~31LL;
 }
 
-struct EncLayout { size_t rec, raw, words, offs, status, total; long long cap_words; };
+struct EncLayout { size_t rec, words, offs, status, total; long long cap_words, n_pad; };
 static EncLayout enc_layout(int n_streams, long long n)
 {
     EncLayout L;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t nt = (size_t)n_streams * n;
+    L.n_pad = (n + 31) & ~31LL;
     L.cap_words = enc_cap_words(n);
     L.rec = 0;
-    L.raw = al(L.rec + nt * sizeof(Record));
-    L.words = al(L.raw + nt * 4);
+    L.words = al(L.rec + (size_t)n_streams * L.n_pad * sizeof(Record));
     L.offs = al(L.words + (size_t)n_streams * L.cap_words * 4);
     L.status = al(L.offs + (size_t)n_streams * 8);
     L.total = al(L.status + (size_t)n_streams * 4);
@@ -576,18 +667,17 @@ extern "C" int icm_rans_encode_batch(const icm_tables *t, const int32_t *d_symbo
     const EncLayout L = enc_layout(n_streams, n_per_stream);
     char *w = (char *)d_work;
     Record *rec = (Record *)(w + L.rec);
-    uint32_t *raw = (uint32_t *)(w + L.raw);
     uint32_t *words = (uint32_t *)(w + L.words);
     long long *offs = (long long *)(w + L.offs);
     int32_t *status = (int32_t *)(w + L.status);
     ICM_CUDA(cudaMemsetAsync(status, 0, (size_t)n_streams * 4, st));
-    const long long nt = (long long)n_streams * n_per_stream;
+    const long long nt = (long long)n_streams * L.n_pad;
     if (nt > 0) {
         const int grid = (int)min((nt + 255) / 256, (long long)sm_count() * 16);
-        rans_records_kernel<<<grid, 256, 0, st>>>(t->dev, d_symbols, d_indexes, nt, n_per_stream, rec, raw, status);
+        rans_records_kernel<<<grid, 256, 0, st>>>(t->dev, d_symbols, d_indexes, n_streams, n_per_stream, L.n_pad, rec, status);
         ICM_LAUNCH_CHECK();
     }
-    rans_encode_kernel<<<n_streams, 32, 0, st>>>(rec, raw, n_per_stream, words, L.cap_words, d_sizes, status);
+    rans_encode_kernel<<<n_streams, 32, 0, st>>>(rec, L.n_pad, words, L.cap_words, d_sizes, status);
     ICM_LAUNCH_CHECK();
     rans_scan_kernel<<<1, 32, 0, st>>>(d_sizes, n_streams, offs, d_sizes + n_streams);
     ICM_LAUNCH_CHECK();
