@@ -25,7 +25,7 @@ namespace icm {
 constexpr int BM = 128;      // pixels per tile == TMEM lanes
 constexpr int BK = 64;       // bf16 channels per k-step == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 
 // ---------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,7 +115,8 @@ struct ConvParams {
     int k_chunks;          // ceil(Cin / 64)
     int Cin_pad;           // channels per tap in the packed weight
     int KH, KW, stride, pad;
-    int BN, Cout, stages, tmem_cols;
+    int BN, Cout, stages, tmem_cols; // tmem_cols = two accumulators
+    int n_tiles, total_tiles;
     int act, out_dtype, pixel_shuffle;
     long long out_pitch, res_pitch;
     const float *bias;
@@ -152,9 +153,18 @@ __device__ __forceinline__ float apply_act(float v, int act)
     return v;
 }
 
-constexpr int CONV_THREADS = 320; // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
+constexpr int CONV_THREADS = (2 + EPI_WARPS) * 32; // TMA warp + MMA warp + epilogue warps
 
-__global__ void __launch_bounds__(CONV_THREADS, 2)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA pipeline runs
+// across tile boundaries, and the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps
+// the loads and MMAs of tile i+1.
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -164,23 +174,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(tiles + (size_t)p.stages * stage_bytes);
     uint64_t *empty_bar = full_bar + MAX_STAGES;
-    uint64_t *accum_bar = empty_bar + MAX_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    uint64_t *acc_full = empty_bar + MAX_STAGES; // [2] MMA -> epilogue
+    uint64_t *acc_empty = acc_full + 2;          // [2] epilogue -> MMA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    int tile = blockIdx.x;
-    const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
-    const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
-    const int b = tile;
     const int TW = 1 << p.TW_log2, TH = BM >> p.TW_log2;
-    const int w0 = tw_i * TW, h0 = th_i * TH;
-    const int n0 = blockIdx.y * p.BN;
     const int k_iters = p.KH * p.KW * p.k_chunks;
+    const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1; // TMEM columns between the two accumulators
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) { // TMEM allocation is warp-collective
@@ -192,6 +197,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile id -> (n tile fastest, then w, h, image)
+    auto tile_coords = [&](int tile, int &n0, int &w0, int &h0, int &b) {
+        const int nt = tile % p.n_tiles; tile /= p.n_tiles;
+        const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+        const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+        n0 = nt * p.BN; w0 = tw_i * TW; h0 = th_i * TH; b = tile;
+    };
+
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
@@ -199,16 +212,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < k_iters; ++it) {
-                const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
-                const int dy = tap / p.KW, dx = tap - dy * p.KW;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                unsigned char *sa = tiles + (size_t)stage * stage_bytes;
-                unsigned char *sb = sa + a_bytes;
-                mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-                tma_load_4d(&map_a, &full_bar[stage], sa, chunk * BK, w0 * p.stride + dx - p.pad, h0 * p.stride + dy - p.pad, b);
-                tma_load_2d(&map_w, &full_bar[stage], sb, tap * p.Cin_pad + chunk * BK, n0);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int n0, w0, h0, b;
+                tile_coords(tile, n0, w0, h0, b);
+                for (int it = 0; it < k_iters; ++it) {
+                    const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
+                    const int dy = tap / p.KW, dx = tap - dy * p.KW;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = tiles + (size_t)stage * stage_bytes;
+                    unsigned char *sb = sa + a_bytes;
+                    mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                    tma_load_4d(&map_a, &full_bar[stage], sa, chunk * BK, w0 * p.stride + dx - p.pad, h0 * p.stride + dy - p.pad, b);
+                    tma_load_2d(&map_w, &full_bar[stage], sb, tap * p.Cin_pad + chunk * BK, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -217,83 +234,103 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
-        for (int it = 0; it < k_iters; ++it) {
-            mbar_wait(&full_bar[stage], phase);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+            const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the 16-byte address field
-                    umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the 16-byte address field
+                        umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
+                    if (it == k_iters - 1) umma_commit(&acc_full[acc]); // accumulator complete
                 }
-                umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
-                if (it == k_iters - 1) umma_commit(accum_bar); // accumulator complete
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..9)
-        const int q = warp & 3;          // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2; // the two warps of a quarter take alternate column chunks
+        // ------------------------------------------------------------------ epilogue (warps 2..17)
+        const int q = warp & 3;           // TMEM lane quarter this warp may read
+        const int grp = (warp - 2) >> 2;  // the four warps of a quarter take column chunks grp, grp+4, ...
         const int r = q * 32 + lane;
         const int th = r >> p.TW_log2, tw = r & (TW - 1);
-        const int oh = h0 + th, ow = w0 + tw;
-        const bool valid = (oh < p.Ho) && (ow < p.Wo);
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
         const int Cq = p.pixel_shuffle ? p.Cout / (p.pixel_shuffle * p.pixel_shuffle) : 0;
-        for (int c16 = half; c16 < p.BN / 16; c16 += 2) {
-            uint32_t acc[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c16 * 16), acc);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int n = n0 + c16 * 16;
-            if (!valid || n >= p.Cout) continue;
-            float v[16];
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int n0, w0, h0, b;
+            tile_coords(tile, n0, w0, h0, b);
+            const int oh = h0 + th, ow = w0 + tw;
+            const bool valid = (oh < p.Ho) && (ow < p.Wo);
+            const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
+            mbar_wait(&acc_full[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+            for (int c16 = grp; c16 < p.BN / 16; c16 += EPI_WARPS / 4) {
+                uint32_t accv[16];
+                tmem_ld16(tmem_d + (uint32_t)(c16 * 16), accv);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int n = n0 + c16 * 16;
+                if (!valid || n >= p.Cout) continue;
+                float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-            if (p.bias) {
-                const float4 *bp = reinterpret_cast<const float4 *>(p.bias + n);
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(accv[j]);
+                if (p.bias) {
+                    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + n);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { const float4 t = __ldg(bp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-            long long off;
-            if (p.pixel_shuffle) {
-                const int rr = p.pixel_shuffle;
-                const int quad = n / Cq, c = n - quad * Cq;
-                const int i = quad / rr, jj = quad - i * rr;
-                off = (((long long)b * p.Ho * rr + (long long)oh * rr + i) * ((long long)p.Wo * rr) + (long long)ow * rr + jj) * p.out_pitch + c;
-            } else {
-                off = pix * p.out_pitch + n;
-            }
-            if (p.residual) {
-                const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix * p.res_pitch + n);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float4 t = __ldg(rp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
-            }
-            if (p.out_dtype == ICM_OUT_F32) {
-                float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                    pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                    for (int j = 0; j < 4; ++j) { const float4 t = __ldg(bp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
                 }
-                uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + off);
-                op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+                long long off;
+                if (p.pixel_shuffle) {
+                    const int rr = p.pixel_shuffle;
+                    const int quad = n / Cq, c = n - quad * Cq;
+                    const int i = quad / rr, jj = quad - i * rr;
+                    off = (((long long)b * p.Ho * rr + (long long)oh * rr + i) * ((long long)p.Wo * rr) + (long long)ow * rr + jj) * p.out_pitch + c;
+                } else {
+                    off = pix * p.out_pitch + n;
+                }
+                if (p.residual) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix * p.res_pitch + n);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float4 t = __ldg(rp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+                }
+                if (p.out_dtype == ICM_OUT_F32) {
+                    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                    }
+                    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + off);
+                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
             }
+            // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -392,18 +429,15 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     // small problems: more, narrower N tiles so that more SMs take part
     const long long m_tiles = (long long)a->B * p.tiles_w * p.tiles_h;
     while (p.BN > 64 && p.BN % 32 == 0 && m_tiles * ((a->Cout + p.BN - 1) / p.BN) * 2 <= sm_count()) p.BN /= 2;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < p.BN) p.tmem_cols *= 2;
+    p.tmem_cols = 64;
+    while (p.tmem_cols < 2 * p.BN) p.tmem_cols *= 2; // two accumulators, power-of-two allocation, <= 512
     const int k_iters = p.KH * p.KW * p.k_chunks;
     const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-    // pipeline depth: never deeper than the K loop; capped so that at least two CTAs fit on an SM
-    // (227 KB shared memory, 512 TMEM columns, 2 x 320 threads)
-    // Long K loops (the 3x3 / 5x5 convolutions) are MMA-bound: give one CTA the whole SM and a deep pipeline.
-    p.stages = (int)(((k_iters >= 16 ? 200 : 110) * 1024) / stage_bytes);
+    // one persistent CTA per SM: the pipeline is as deep as shared memory allows and runs across tiles
+    p.stages = (int)((200 * 1024) / stage_bytes);
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    if (p.stages > k_iters) p.stages = k_iters;
-    if (p.stages < 2) p.stages = k_iters < 2 ? 1 : 2;
+    if (p.stages < 2) p.stages = 2;
     p.act = a->act; p.out_dtype = a->out_dtype; p.pixel_shuffle = ps;
     p.out_pitch = a->out_pitch; p.res_pitch = a->res_pitch;
     p.bias = a->bias; p.residual = a->residual; p.out = a->out;
@@ -434,14 +468,16 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("icm_conv2d: cuTensorMapEncodeTiled(W) failed (%d)", (int)r); return ICM_ERR_CUDA; }
     }
-    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 1) * 8 + 16;
+    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
     static thread_local size_t configured = 0;
     if (smem_bytes > configured) {
         ICM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = 227 * 1024;
     }
-    ICM_CHECK_ARG(m_tiles <= 0x7FFFFFFF, "icm_conv2d: too many tiles");
-    dim3 grid((unsigned)m_tiles, (a->Cout + p.BN - 1) / p.BN);
+    p.n_tiles = (a->Cout + p.BN - 1) / p.BN;
+    ICM_CHECK_ARG(m_tiles * p.n_tiles <= 0x7FFFFFFF, "icm_conv2d: too many tiles");
+    p.total_tiles = (int)(m_tiles * p.n_tiles);
+    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
     conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
