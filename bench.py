@@ -211,9 +211,10 @@ def main():
     ms, launches, last = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
     c_last = last[0]
-    for packed, sizes in c_last["strings"]:  # deferred status check of the device-resident streams
-        if int(sizes.min()) < 0:
-            raise RuntimeError("rANS encoder reported an error status")
+    for group in c_last["strings"]:  # deferred status check of the device-resident streams
+        for packed, sizes in group:
+            if int(sizes.min()) < 0:
+                raise RuntimeError("rANS encoder reported an error status")
     step_e2e()
     ms_e2e, _, c_e2e = timed(step_e2e, args.steps)
     n_img = B * world * args.steps

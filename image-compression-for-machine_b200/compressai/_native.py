@@ -43,7 +43,7 @@ class Profile:
 
     _HOST = {"icm_last_error", "icm_abi_version", "icm_launch_count", "icm_pmf_to_quantized_cdf", "icm_tables_create",
              "icm_tables_destroy", "icm_rans_encode_workspace_bytes", "icm_rans_decoder_create", "icm_rans_decoder_destroy",
-             "icm_rans_decoder_set_streams", "icm_rans_decoder_status"}
+             "icm_rans_decoder_set_streams", "icm_rans_decoder_status", "icm_set_conv_sm_limit"}
 
     def __init__(self):
         self.records = {}
@@ -139,6 +139,7 @@ def _load():
         "icm_add_lrp": (I, [View, View, I, I, I64, View, View, P]),
         "icm_eb_process": (I, [I, View, I, I, I64, P, F, P, P, View, View, View, P]),
         "icm_conv2d": (I, [C.POINTER(ConvArgs), P]),
+        "icm_set_conv_sm_limit": (I, [I]),
         "icm_pack_conv_weight": (I, [P, I, I, I, I, I, I, I, P, P]),
         "icm_layernorm": (I, [P, P, P, P, I, I64, I, I, I, I, I, P]),
         "icm_cast_bf16": (I, [P, I64, I, I64, P, I64, P]),

@@ -110,7 +110,7 @@ _workspaces = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index, "enc")
+    key = (device.index, torch.cuda.current_stream().cuda_stream)  # one per stream: micro-batches run concurrently
     w = _workspaces.get(key)
     if w is None or w.numel() < nbytes:
         w = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
@@ -158,6 +158,40 @@ def encode_streams(tables, symbols, indexes, return_device=False):
         out.append(host[o:o + v])
         o += v
     return out
+
+
+def strings_to_host(packed, sizes, retry=None):
+    """Device-resident streams (packed uint8, int32 sizes[S+1]) -> list of S `bytes`.  `retry()` re-encodes with
+    the worst-case capacity when the optimistic output buffer of the asynchronous encode was too small."""
+    hs = sizes.cpu().tolist()
+    S = len(hs) - 1
+    if any(v == _ERR_BAD_INDEX for v in hs[:S]):
+        raise ValueError("encode_with_indexes: CDF index out of range")
+    if any(v < 0 for v in hs[:S]):
+        if retry is None:
+            raise NativeError("rANS output exceeded the buffer capacity")
+        return retry()
+    total = sum(hs[:S])
+    host = packed[:total].cpu().numpy().tobytes()
+    out, o = [], 0
+    for v in hs[:S]:
+        out.append(host[o:o + v])
+        o += v
+    return out
+
+
+_decoder_pool = {}
+
+
+def acquire_decoder(n_streams):
+    """A StreamDecoder from a per-size pool.  Creating / destroying one costs a cudaMalloc / cudaFree, and
+    cudaFree synchronises the whole device, which would serialise concurrently running micro-batches."""
+    free = _decoder_pool.setdefault((int(n_streams), torch.cuda.current_device()), [])
+    return free.pop() if free else StreamDecoder(n_streams)
+
+
+def release_decoder(dec):
+    _decoder_pool.setdefault((dec.n_streams, torch.cuda.current_device()), []).append(dec)
 
 
 class StreamDecoder:

@@ -341,6 +341,8 @@ class EntropyBottleneck(EntropyModel):
             self._packed = torch.cat(parts, 1).float().contiguous()
             assert self._packed.shape[1] == _native.EB_PARAMS
             self._packed_key = key
+            if self._packed.is_cuda:
+                torch.cuda.current_stream().synchronize()  # ready before another stream may read it
         return self._packed
 
     def forward(self, x: Tensor, training: Optional[bool] = None) -> Tuple[Tensor, Tensor]:

@@ -40,9 +40,11 @@ class Engine:
     def __init__(self, model):
         self.model = model
         self._packed = {}
+        self.warm = False  # True once every weight has been packed (first full run): micro-batching may start
 
     def invalidate(self):
         self._packed.clear()
+        self.warm = False
 
     # ---------------------------------------------------------------------------------- weights
     def packed(self, module, ps=0):
@@ -57,6 +59,7 @@ class Engine:
             else:
                 raise TypeError(type(module))
             self._packed[key] = (pk, module)  # holding the module keeps its id() from being reused
+            torch.cuda.current_stream().synchronize()  # packed before any other stream may use it (micro-batches)
         return pk
 
     def f32(self, p):
@@ -65,6 +68,7 @@ class Engine:
         if hit is None:
             hit = (p.detach().float().contiguous(), p)
             self._packed[key] = hit
+            torch.cuda.current_stream().synchronize()
         return hit[0]
 
     # ---------------------------------------------------------------------------------- kernels

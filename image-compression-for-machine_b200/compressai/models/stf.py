@@ -304,13 +304,57 @@ class SymmetricalTransFormer(CompressionModel):
         x_hat = self._synthesis(y_hat, B, h, w, clamp=False)
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
 
-    @torch.no_grad()
-    def compress(self, x, device_strings=False):
-        """stf.py:671-732.  Returns {"strings": [[y_0..y_{B-1}], [z_0..z_{B-1}]], "shape": (h/4, w/4)}.
+    # ---------------------------------------------------------------------------------- micro-batching
+    # The two rANS coders are latency-bound (one warp per image stream), the transforms are throughput-bound.
+    # A batch is therefore split into `micro_batches` parts that run on their own CUDA streams, so that the
+    # coder of one part overlaps the convolutions of another; the conv kernel is told to leave the coder's SMs
+    # alone (icm_set_conv_sm_limit).  Results are identical to the unsplit run (kernels are batch-invariant).
+    micro_batches = 2
+    micro_batch_min = 16  # only split batches at least this large
 
-        device_strings=True keeps the streams on the GPU: "strings" is then [(packed_y, sizes_y), (packed_z, sizes_z)]
-        (uint8 / int32 CUDA tensors, no host synchronisation), which decompress() accepts as is."""
-        self._check_input(x)
+    def _part_ranges(self, B):
+        n = self.micro_batches if B >= self.micro_batch_min else 1
+        n = max(1, min(n, B))
+        base, extra = divmod(B, n)
+        out, lo = [], 0
+        for i in range(n):
+            hi = lo + base + (1 if i < extra else 0)
+            out.append((lo, hi))
+            lo = hi
+        return out
+
+    def _run_parts(self, fns, coder_streams):
+        """Run the callables on side streams (one each), joined back into the current stream."""
+        if len(fns) == 1:
+            return [fns[0]()]
+        cur = torch.cuda.current_stream()
+        pool = getattr(self, "_side_streams", None)
+        if pool is None or len(pool) < len(fns) or pool[0].device != cur.device:
+            pool = [torch.cuda.Stream(device=cur.device) for _ in fns]
+            self._side_streams = pool
+        sms = torch.cuda.get_device_properties(cur.device).multi_processor_count
+        check(lib().icm_set_conv_sm_limit(max(sms // 2, sms - coder_streams)), "icm_set_conv_sm_limit")
+        outs = []
+        try:
+            for st, fn in zip(pool, fns):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    outs.append(fn())
+            for st in pool[:len(fns)]:
+                cur.wait_stream(st)
+        finally:
+            check(lib().icm_set_conv_sm_limit(0), "icm_set_conv_sm_limit")
+        return outs
+
+    @staticmethod
+    def _hand_over(t):
+        """A tensor produced on a side stream is consumed on the current stream from now on."""
+        if isinstance(t, torch.Tensor):
+            t.record_stream(torch.cuda.current_stream())
+        return t
+
+    def _compress_part(self, x):
+        """compress() of one micro-batch, fully asynchronous: device-resident streams."""
         eb = self.entropy_bottleneck
         B = x.shape[0]
         y, h, w = self._analysis(x)
@@ -324,39 +368,82 @@ class SymmetricalTransFormer(CompressionModel):
               "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
         _, sym, idx = self._slice_loop("compress", B, h, w, mean_sup, scale_sup, y=y)
-        mode = "async" if device_strings else False
-        z_strings = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device=mode)
-        y_strings = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device=mode)
-        return {"strings": [y_strings, z_strings], "shape": torch.Size([zh, zw])}
+        z_str = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device="async")
+        y_str = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device="async")
+        return {"y": y_str, "z": z_str, "shape": (zh, zw), "retry": (sym, idx, z_sym, z_idx)}
 
     @torch.no_grad()
-    def decompress(self, strings, shape):
-        """stf.py:734-785 for any batch size: strings = [[y strings], [z strings]], one of each per image."""
-        assert isinstance(strings, list) and len(strings) == 2
+    def compress(self, x, device_strings=False):
+        """stf.py:671-732.  Returns {"strings": [[y_0..y_{B-1}], [z_0..z_{B-1}]], "shape": (h/4, w/4)}.
+
+        device_strings=True keeps the streams on the GPU: "strings" is then [[(packed_y, sizes_y), ...], [(packed_z,
+        sizes_z), ...]] with one (uint8, int32) CUDA tensor pair per micro-batch and no host synchronisation;
+        decompress() accepts that form as is."""
+        self._check_input(x)
+        B = x.shape[0]
+        parts = self._part_ranges(B)
+        outs = self._run_parts([(lambda lo=lo, hi=hi: self._compress_part(x[lo:hi])) for lo, hi in parts], coder_streams=parts[0][1] - parts[0][0])
+        shape = torch.Size(outs[0]["shape"])
+        for o in outs:
+            for k in ("y", "z"):
+                self._hand_over(o[k][0]); self._hand_over(o[k][1])
+        if device_strings:
+            return {"strings": [[o["y"] for o in outs], [o["z"] for o in outs]], "shape": shape}
+        gc_t, eb_t = self.gaussian_conditional.device_tables(), self.entropy_bottleneck.device_tables()
+        y_strings, z_strings = [], []
+        for o in outs:
+            sym, idx, z_sym, z_idx = o["retry"]
+            y_strings += ans.strings_to_host(*o["y"], retry=lambda: ans.encode_streams(gc_t, sym, idx))
+            z_strings += ans.strings_to_host(*o["z"], retry=lambda: ans.encode_streams(eb_t, z_sym, z_idx))
+        return {"strings": [y_strings, z_strings], "shape": shape}
+
+    def _decompress_part(self, y_str, z_str, B, zh, zw, on_device):
         eb = self.entropy_bottleneck
         dev = eb.quantiles.device
-        if dev.type != "cuda":
-            raise NativeError("SymmetricalTransFormer runs on CUDA only (no CPU fallback)")
-        y_strings, z_strings = strings
-        on_device = isinstance(z_strings, tuple)
-        B = z_strings[1].numel() - 1 if on_device else len(z_strings)
-        if not on_device and len(y_strings) != B:
-            raise ValueError("need one y-string and one z-string per image")
-        zh, zw = int(shape[0]), int(shape[1])
         Pz = zh * zw
         h, w = 4 * zh, 4 * zw
-        zdec = ans.StreamDecoder(B)
-        zdec.set_streams_device(*z_strings) if on_device else zdec.set_streams(z_strings)
+        zdec = ans.acquire_decoder(B)
+        zdec.set_streams_device(*z_str) if on_device else zdec.set_streams(z_str)
         z_idx = torch.arange(192, dtype=torch.int32, device=dev).repeat_interleave(Pz).repeat(B, 1)
         z_sym = zdec.decode_step(eb.device_tables(), z_idx)
         z_hat = torch.empty((B * Pz, 192), dtype=torch.bfloat16, device=dev)
         check(lib().icm_eb_process(2, NULL_VIEW, B, 192, Pz, eb.packed_params().data_ptr(), 0.0, z_sym.data_ptr(), None,
                                    NULL_VIEW, view_bcp(z_hat, B, 192, Pz), NULL_VIEW, stream_ptr()), "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
-        ydec = ans.StreamDecoder(B)
-        ydec.set_streams_device(*y_strings) if on_device else ydec.set_streams(y_strings)
+        ydec = ans.acquire_decoder(B)
+        ydec.set_streams_device(*y_str) if on_device else ydec.set_streams(y_str)
         y_hat, _, _ = self._slice_loop("decompress", B, h, w, mean_sup, scale_sup, decoder=ydec)
-        if not on_device:  # (status is a host read; the device-resident path leaves it to the caller)
-            zdec.check_status()
-            ydec.check_status()
-        return {"x_hat": self._synthesis(y_hat, B, h, w, clamp=True)}
+        x_hat = self._synthesis(y_hat, B, h, w, clamp=True)
+        return x_hat, (zdec, ydec)
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        """stf.py:734-785 for any batch size: strings = [[y strings], [z strings]], one of each per image
+        (or the device-resident form produced by compress(..., device_strings=True))."""
+        assert isinstance(strings, list) and len(strings) == 2
+        eb = self.entropy_bottleneck
+        dev = eb.quantiles.device
+        if dev.type != "cuda":
+            raise NativeError("SymmetricalTransFormer runs on CUDA only (no CPU fallback)")
+        y_strings, z_strings = strings
+        zh, zw = int(shape[0]), int(shape[1])
+        on_device = len(z_strings) > 0 and isinstance(z_strings[0], tuple)
+        if on_device:
+            jobs = [(y, z, z[1].numel() - 1) for y, z in zip(y_strings, z_strings)]
+        else:
+            if len(y_strings) != len(z_strings):
+                raise ValueError("need one y-string and one z-string per image")
+            jobs = [(y_strings[lo:hi], z_strings[lo:hi], hi - lo) for lo, hi in self._part_ranges(len(z_strings))]
+        outs = self._run_parts([(lambda y=y, z=z, n=n: self._decompress_part(y, z, n, zh, zw, on_device)) for y, z, n in jobs],
+                               coder_streams=jobs[0][2])
+        xs = [self._hand_over(o[0]) for o in outs]
+        try:
+            if not on_device:  # (status is a host read; the device-resident path leaves it to the caller)
+                for _, decs in outs:
+                    for d in decs:
+                        d.check_status()
+        finally:
+            for _, decs in outs:
+                for d in decs:
+                    ans.release_decoder(d)
+        return {"x_hat": xs[0] if len(xs) == 1 else torch.cat(xs, 0)}

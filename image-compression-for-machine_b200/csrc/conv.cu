@@ -393,9 +393,21 @@ static int pick_tile_w_log2(int Ho, int Wo)
     return best_l;
 }
 
+static thread_local int g_sm_limit = 0;
+
 }  // namespace icm
 
 using namespace icm;
+
+// Cap on the number of persistent CTAs (= SMs) icm_conv2d may occupy, 0 = all.  Used when another stream runs
+// the rANS coders at the same time: their one-warp CTAs hold ~155 KB of shared memory each and cannot share
+// an SM with a conv CTA, so the conv grid leaves them room instead of queueing behind them.
+extern "C" int icm_set_conv_sm_limit(int n_sms)
+{
+    ICM_CHECK_ARG(n_sms >= 0, "icm_set_conv_sm_limit: negative limit");
+    g_sm_limit = n_sms;
+    return ICM_OK;
+}
 
 extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
 {
@@ -477,7 +489,9 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.n_tiles = (a->Cout + p.BN - 1) / p.BN;
     ICM_CHECK_ARG(m_tiles * p.n_tiles <= 0x7FFFFFFF, "icm_conv2d: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
-    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    int max_ctas = sm_count();
+    if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
+    const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
     conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
     ICM_LAUNCH_CHECK();
     return ICM_OK;

@@ -169,6 +169,8 @@ typedef struct {
     int res_pitch;
 } icm_conv_args;
 int icm_conv2d(const icm_conv_args *a, void *stream);
+/* Cap on the SMs icm_conv2d occupies (0 = all), for overlap with the rANS coders on another stream. */
+int icm_set_conv_sm_limit(int n_sms);
 int icm_pack_conv_weight(const float *d_w_oihw, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,
                          int pixel_shuffle, void *d_out_bf16, void *stream);
 

@@ -107,6 +107,28 @@ def test_batch_strings_equal_single_image_strings(model):
         assert torch.equal(d1["x_hat"][0], db["x_hat"][b])
 
 
+def test_micro_batched_streams_give_identical_results(model):
+    """Large batches are split over CUDA streams so the coders overlap the transforms; the split must not
+    change a single byte, and the device-resident hand-off must decode to the same images."""
+    from oracle import weights
+
+    xs = torch.cat([weights.seeded_image((1, 3, 64, 128), seed=10 + s) for s in range(17)]).cuda()
+    assert len(model._part_ranges(17)) == 2
+    split = model.compress(xs)
+    model.micro_batches = 1
+    try:
+        whole = model.compress(xs)
+        d_whole = model.decompress(whole["strings"], whole["shape"])
+    finally:
+        model.micro_batches = 2
+    assert split["strings"] == whole["strings"]
+    d_split = model.decompress(split["strings"], split["shape"])
+    assert torch.equal(d_split["x_hat"], d_whole["x_hat"])
+    dev = model.compress(xs, device_strings=True)
+    d_dev = model.decompress(dev["strings"], dev["shape"])
+    assert torch.equal(d_dev["x_hat"], d_whole["x_hat"])
+
+
 def test_strings_decode_with_the_cpu_oracle(model, x):
     """Cross-implementation check: the GPU-produced y-string of an image decodes, with the pinned CPU coder
     and the GPU-side indexes, to the symbols the GPU encoder consumed."""
