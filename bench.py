@@ -92,6 +92,11 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+def pipe_capacity_bytes(B):
+    """Bytes of bit-stream buffers that cross PCIe per step in the e2e path (fixed-capacity y and z buffers)."""
+    return B * ((2 * 589824 + 64) + (2 * 18432 + 64) + 8)
+
+
 def cpu_reference_step(sd, x, tabs):
     """One compress + decompress of the images in x on the host: the CPU restatement of the reference path."""
     from oracle import stf_ref
@@ -125,13 +130,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--weights", default="default", choices=sorted(WEIGHTS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams of the codec pipeline")
+    ap.add_argument("--part", type=int, default=16, help="images per pipeline job")
+    ap.add_argument("--dec-per-cta", type=int, default=4, help="rANS decoder streams per CTA in the pipeline (1, 2, 4)")
+    ap.add_argument("--conv-sms", type=int, default=-1, help="cap on SMs used by the conv kernel (0 = all, -1 = automatic)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"stf 3x{H_IMG}x{W_IMG}, {args.batch} images per GPU per step (BASELINE.json configs[2]; batch sharded, no collective)"
     config = {"workload": workload, "images_per_gpu": args.batch, "height": H_IMG, "width": W_IMG,
-              "weights": WEIGHTS[args.weights], "l2": "inputs larger than L2 (302 MB per batch at B=64)"}
+              "weights": WEIGHTS[args.weights], "l2": "inputs larger than L2 (302 MB per batch at B=64)",
+              "pipeline": f"{args.streams} CUDA streams x jobs of {args.part} images (compress -> decompress per job), K steps in flight"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -169,17 +180,20 @@ def main():
     x_dev = x_host.to(dev)
     out_host = torch.empty((B, 3, H_IMG, W_IMG), dtype=torch.float32).pin_memory()
 
-    def step_device():
-        c = model.compress(x_dev, device_strings=True)
-        return c, model.decompress(c["strings"], c["shape"])
+    from compressai.utils.pipeline import RoundTripPipeline
 
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        c = model.compress(xd)                       # -> Python bytes on the host
-        d = model.decompress(c["strings"], c["shape"])
-        out_host.copy_(d["x_hat"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return c
+    pipe = RoundTripPipeline(model, n_streams=args.streams, part=min(args.part, B), conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
+                             decoder_streams_per_cta=args.dec_per_cta)
+    out_bufs = [out_host, torch.empty_like(out_host).pin_memory()] if not args.no_e2e else []
+
+    def run_device(steps):
+        """K steps = K batches through the stream pipeline, images and bit-streams resident in HBM."""
+        return pipe.roundtrip([x_dev] * steps)
+
+    def run_e2e(steps):
+        """K steps through the host-facing path: pinned images -> H2D -> compress -> streams to the host and back
+        -> decompress -> x_hat -> pinned host buffers; returns the Python byte strings of every image."""
+        return pipe.roundtrip([x_host] * steps, host_io=True, out_host=[out_bufs[i % 2] for i in range(steps)])
 
     def barrier():
         torch.cuda.synchronize()
@@ -187,42 +201,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, wall=False):
         barrier()
         l0 = _native.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
-        for _ in range(steps):
-            r = fn()
+        r = fn(steps)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = (time.perf_counter() - t0) * 1e3 if wall else e0.elapsed_time(e1)
         launches = _native.launch_count() - l0
         ms = max_over_ranks(ms, device=dev)
         barrier()
         return ms, launches, r
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    run_device(max(args.warmup, 3))
+    torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    ms, launches, last = timed(step_device, args.steps)
+    ms, launches, _ = timed(run_device, args.steps)
     clocks = sampler.stop() if sampler else None
-    c_last = last[0]
-    for group in c_last["strings"]:  # deferred status check of the device-resident streams
-        for packed, sizes in group:
-            if int(sizes.min()) < 0:
-                raise RuntimeError("rANS encoder reported an error status")
-    step_e2e()
-    ms_e2e, _, c_e2e = timed(step_e2e, args.steps)
     n_img = B * world * args.steps
     value = n_img / (ms / 1e3)
-    e2e_value = n_img / (ms_e2e / 1e3)
-    str_bytes = sum(len(s) for grp in c_e2e["strings"] for s in grp)
-    h2d = x_host.numel() * 4 + str_bytes
-    d2h = out_host.numel() * 4 + str_bytes
+    e2e = None
+    str_bytes = 0
+    if not args.no_e2e:
+        run_e2e(2)
+        ms_e2e, _, (_, strings) = timed(run_e2e, args.steps, wall=True)
+        str_bytes = sum(len(s) for grp in strings[0] for s in grp)
+        e2e = {"value": round(n_img / (ms_e2e / 1e3), 3), "unit": "images/s",
+               "h2d_bytes_per_step": x_host.numel() * 4 + pipe_capacity_bytes(B),
+               "d2h_bytes_per_step": out_host.numel() * 4 + pipe_capacity_bytes(B), "ms_per_step": round(ms_e2e / args.steps, 3),
+               "timing": "wall clock around K pipelined steps incl. creation of the Python byte strings"}
 
     # instrumented step: per-entry-point CUDA events -> dominant kernel family and its roofline
     roofline, families = None, None
@@ -232,8 +245,10 @@ def main():
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except Exception:  # noqa: BLE001
             pass
-        with _native.Profile() as prof:
-            step_device()
+        model.micro_batches = 1
+        with _native.Profile() as prof:  # plain API, one stream: clean per-kernel times
+            c = model.compress(x_dev, device_strings=True)
+            model.decompress(c["strings"], c["shape"])
             summ = prof.summary()
         total_ms = sum(v[1] for v in summ.values())
         families = {k: {"calls": v[0], "ms": round(v[1], 3), "share": round(v[1] / total_ms, 4)} for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
@@ -261,8 +276,7 @@ def main():
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 operands / fp32 accumulate (transforms); fp32 (entropy models); u64 (rANS)", "data": "synthetic",
             "config": config, "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "e2e": e2e,
             "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "families": families,
             "msym_per_s": round(value * SYMBOLS_PER_IMAGE / 1e6, 2),
             "bytes_per_image": round(str_bytes / B, 1),

@@ -307,8 +307,8 @@ class SymmetricalTransFormer(CompressionModel):
     # ---------------------------------------------------------------------------------- micro-batching
     # The two rANS coders are latency-bound (one warp per image stream), the transforms are throughput-bound.
     # A batch is therefore split into `micro_batches` parts that run on their own CUDA streams, so that the
-    # coder of one part overlaps the convolutions of another; the conv kernel is told to leave the coder's SMs
-    # alone (icm_set_conv_sm_limit).  Results are identical to the unsplit run (kernels are batch-invariant).
+    # coder of one part overlaps the convolutions of another (the conv kernel's dynamic tile scheduler
+    # tolerates SMs that are held by coder CTAs).  Results are identical to the unsplit run (kernels are batch-invariant).
     micro_batches = 2
     micro_batch_min = 16  # only split batches at least this large
 
@@ -332,18 +332,13 @@ class SymmetricalTransFormer(CompressionModel):
         if pool is None or len(pool) < len(fns) or pool[0].device != cur.device:
             pool = [torch.cuda.Stream(device=cur.device) for _ in fns]
             self._side_streams = pool
-        sms = torch.cuda.get_device_properties(cur.device).multi_processor_count
-        check(lib().icm_set_conv_sm_limit(max(sms // 2, sms - coder_streams)), "icm_set_conv_sm_limit")
         outs = []
-        try:
-            for st, fn in zip(pool, fns):
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    outs.append(fn())
-            for st in pool[:len(fns)]:
-                cur.wait_stream(st)
-        finally:
-            check(lib().icm_set_conv_sm_limit(0), "icm_set_conv_sm_limit")
+        for st, fn in zip(pool, fns):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(fn())
+        for st in pool[:len(fns)]:
+            cur.wait_stream(st)
         return outs
 
     @staticmethod
@@ -397,12 +392,12 @@ class SymmetricalTransFormer(CompressionModel):
             z_strings += ans.strings_to_host(*o["z"], retry=lambda: ans.encode_streams(eb_t, z_sym, z_idx))
         return {"strings": [y_strings, z_strings], "shape": shape}
 
-    def _decompress_part(self, y_str, z_str, B, zh, zw, on_device):
+    def _decompress_part(self, y_str, z_str, B, zh, zw, on_device, decoders=None):
         eb = self.entropy_bottleneck
         dev = eb.quantiles.device
         Pz = zh * zw
         h, w = 4 * zh, 4 * zw
-        zdec = ans.acquire_decoder(B)
+        zdec = decoders[0] if decoders is not None else ans.acquire_decoder(B)
         zdec.set_streams_device(*z_str) if on_device else zdec.set_streams(z_str)
         z_idx = torch.arange(192, dtype=torch.int32, device=dev).repeat_interleave(Pz).repeat(B, 1)
         z_sym = zdec.decode_step(eb.device_tables(), z_idx)
@@ -410,7 +405,7 @@ class SymmetricalTransFormer(CompressionModel):
         check(lib().icm_eb_process(2, NULL_VIEW, B, 192, Pz, eb.packed_params().data_ptr(), 0.0, z_sym.data_ptr(), None,
                                    NULL_VIEW, view_bcp(z_hat, B, 192, Pz), NULL_VIEW, stream_ptr()), "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
-        ydec = ans.acquire_decoder(B)
+        ydec = decoders[1] if decoders is not None else ans.acquire_decoder(B)
         ydec.set_streams_device(*y_str) if on_device else ydec.set_streams(y_str)
         y_hat, _, _ = self._slice_loop("decompress", B, h, w, mean_sup, scale_sup, decoder=ydec)
         x_hat = self._synthesis(y_hat, B, h, w, clamp=True)

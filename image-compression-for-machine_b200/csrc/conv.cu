@@ -399,9 +399,10 @@ static thread_local int g_sm_limit = 0;
 
 using namespace icm;
 
-// Cap on the number of persistent CTAs (= SMs) icm_conv2d may occupy, 0 = all.  Used when another stream runs
-// the rANS coders at the same time: their one-warp CTAs hold ~155 KB of shared memory each and cannot share
-// an SM with a conv CTA, so the conv grid leaves them room instead of queueing behind them.
+// Cap on the number of persistent CTAs (= SMs) icm_conv2d may occupy, 0 = all.  Used when other streams run
+// the rANS decoder at the same time: its CTAs hold ~155 KB of shared memory each and cannot share an SM with
+// a conv CTA, so the conv grid leaves them room instead of queueing behind them (tiles are assigned to the
+// persistent CTAs statically, so a CTA that starts late delays the whole launch).
 extern "C" int icm_set_conv_sm_limit(int n_sms)
 {
     ICM_CHECK_ARG(n_sms >= 0, "icm_set_conv_sm_limit: negative limit");

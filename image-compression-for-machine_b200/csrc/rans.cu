@@ -409,7 +409,9 @@ __device__ __noinline__ SlowRet dec_slow(DecState d, DecCtx c, SlowArgs a, uint3
     return r;
 }
 
-__global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint32_t *__restrict__ words,
+constexpr int kDecWarps = 4; // max streams per CTA: one per SM sub-partition, sharing the tables in shared memory
+
+__global__ void __launch_bounds__(kDecWarps * 32) rans_decode_kernel(TablesDev T, int n_streams, const uint32_t *__restrict__ words,
                                                          const int64_t *__restrict__ word_off,
                                                          const int64_t *__restrict__ nwords_arr,
                                                          uint64_t *__restrict__ state, int64_t *__restrict__ pos_arr,
@@ -420,18 +422,22 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint
     uint32_t *s_cdf = reinterpret_cast<uint32_t *>(smem_raw);
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_cdf + ((T.total_pad + 3) & ~3));
     uint4 *s_meta = reinterpret_cast<uint4 *>(s_lut + ((size_t)T.n_cdf << T.lut_bits)); // per table
-    __shared__ __align__(16) uint4 s_sym[64]; // per symbol: two chunks of 32
-    __shared__ int32_t s_val[32];
-    const int lane = threadIdx.x;
+    __shared__ __align__(16) uint4 s_sym_all[kDecWarps][64]; // per warp, per symbol: two chunks of 32
+    __shared__ int32_t s_val_all[kDecWarps][32];
+    // warp index broadcast from lane 0: tells the compiler it is warp-uniform (no divergence guards in the loop)
+    const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    uint4 *s_sym = s_sym_all[wid];
+    int32_t *s_val = s_val_all[wid];
     const uint32_t cdf_addr = smem_addr(s_cdf), lut_addr = smem_addr(s_lut), sym_addr = smem_addr(s_sym), val_addr = smem_addr(s_val);
     {
+        const int tid = threadIdx.x, nthr = blockDim.x;
         const uint4 *g = reinterpret_cast<const uint4 *>(T.cdf_pad);
         uint4 *d = reinterpret_cast<uint4 *>(s_cdf);
-        for (int i = lane; i < (T.total_pad + 3) / 4; i += 32) d[i] = __ldg(g + i);
+        for (int i = tid; i < (T.total_pad + 3) / 4; i += nthr) d[i] = __ldg(g + i);
         const uint4 *gl = reinterpret_cast<const uint4 *>(T.lut);
         uint4 *dl = reinterpret_cast<uint4 *>(s_lut);
-        for (int i = lane; i < (int)(((size_t)T.n_cdf << T.lut_bits) / 8); i += 32) dl[i] = __ldg(gl + i);
-        for (int i = lane; i < T.n_cdf; i += 32) {
+        for (int i = tid; i < (int)(((size_t)T.n_cdf << T.lut_bits) / 8); i += nthr) dl[i] = __ldg(gl + i);
+        for (int i = tid; i < T.n_cdf; i += nthr) {
             // per table: {speculative window address, s0 + offset - 1, size - 1 - s0 (the p that means "escape"), t | s0 << 16}
             const int size = T.sizes[i], off = T.offsets[i], base = T.base[i];
             int s0 = 0;
@@ -440,9 +446,10 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(TablesDev T, const uint
                                    (uint32_t)i | ((uint32_t)s0 << 16));
         }
     }
-    __syncwarp();
+    __syncthreads();
 
-    const int s = blockIdx.x;
+    const int s = blockIdx.x * (int)(blockDim.x >> 5) + wid; // the host launches full CTAs only (no early exit:
+                                                              // the compiler must see a converged warp)
     DecCtx ctx;
     ctx.W = words + word_off[s];
     ctx.nwords = (uint32_t)min((long long)nwords_arr[s], 0xFFFFFFFFLL);
@@ -747,6 +754,17 @@ extern "C" int icm_rans_decoder_set_streams_device(icm_rans_decoder *d, const ui
     return ICM_OK;
 }
 
+// Streams per decoder CTA (1, 2 or 4; 0 = automatic).  One stream per CTA is fastest per stream (a whole SM to
+// itself); more streams per CTA share one copy of the tables in shared memory and leave more SMs to other
+// kernels -- what a pipeline that overlaps the decoder with the convolutions wants.
+static thread_local int g_dec_warps = 0;
+extern "C" int icm_set_decoder_streams_per_cta(int n)
+{
+    ICM_CHECK_ARG(n == 0 || n == 1 || n == 2 || n == 4, "icm_set_decoder_streams_per_cta: %d is not 0, 1, 2 or 4", n);
+    g_dec_warps = n;
+    return ICM_OK;
+}
+
 extern "C" int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, const int32_t *d_indexes,
                                      int64_t n_per_stream, int32_t *d_out, void *stream)
 {
@@ -758,8 +776,11 @@ extern "C" int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, c
         ICM_CUDA(cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem_bytes));
         configured = t->smem_bytes;
     }
-    rans_decode_kernel<<<d->n_streams, 32, t->smem_bytes, as_stream(stream)>>>(
-        t->dev, d->d_words, d->d_word_off, d->d_nwords, d->d_state, d->d_pos, d_indexes, n_per_stream, d_out, d->d_status);
+    int warps = g_dec_warps;
+    if (warps == 0) warps = d->n_streams <= sm_count() / 2 ? 1 : (d->n_streams <= sm_count() ? 2 : 4);
+    while (d->n_streams % warps) warps >>= 1; // full CTAs only
+    rans_decode_kernel<<<(d->n_streams + warps - 1) / warps, warps * 32, t->smem_bytes, as_stream(stream)>>>(
+        t->dev, d->n_streams, d->d_words, d->d_word_off, d->d_nwords, d->d_state, d->d_pos, d_indexes, n_per_stream, d_out, d->d_status);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }

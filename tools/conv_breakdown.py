@@ -17,6 +17,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     dev = torch.device("cuda", 0)
     model = bench.make_model(dev)
+    model.micro_batches = 1
     x = bench.make_images(B, 0).to(dev)
     for _ in range(2):
         c = model.compress(x, device_strings=True)
