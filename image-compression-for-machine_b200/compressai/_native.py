@@ -11,7 +11,8 @@ import torch
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "lib", "libicm_b200.so")
 
-ACT_NONE, ACT_GELU, ACT_HALF_TANH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_HALF_TANH, ACT_SIGMOID, ACT_RSQRT, ACT_SQRT = 0, 1, 2, 3, 4, 5
+RES_ADD, RES_ADD_BEFORE_ACT, RES_MUL = 0, 1, 2
 OUT_BF16, OUT_F32 = 0, 1
 EB_PARAMS = 59
 
@@ -30,6 +31,7 @@ class ConvArgs(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("in_pitch", C.c_int),
         ("Cout", C.c_int), ("out_pitch", C.c_int), ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
         ("act", C.c_int), ("out_dtype", C.c_int), ("pixel_shuffle", C.c_int), ("res_pitch", C.c_int),
+        ("res_dtype", C.c_int), ("res_mode", C.c_int),
     ]
 
 
@@ -147,6 +149,11 @@ def _load():
         "icm_window_attention": (I, [P, P, P, I, I, I, I, I, I, I, P]),
         "icm_patch_embed": (I, [P, P, P, P, P, P, I, I, I, I, P]),
         "icm_final_conv": (I, [P, P, P, P, I, I, I, I, I, P]),
+        "icm_image_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
+        "icm_nhwc_to_image": (I, [P, P, I, I, I, I, I, I, P]),
+        "icm_eltwise_bf16": (I, [I, P, I64, P, I64, P, I64, P, I64, I64, I, P]),
+        "icm_window_attention_wacnn": (I, [P, P, P, I, I, I, I, I, I, I, P]),
+        "icm_pack_deconv_weight": (I, [P, I, I, I, I, P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library out of sync

@@ -1,4 +1,5 @@
 from .base import CompressionModel
+from .cnn import WACNN, WACNN2
 from .stf import SymmetricalTransFormer
 
-__all__ = ["CompressionModel", "SymmetricalTransFormer"]
+__all__ = ["CompressionModel", "SymmetricalTransFormer", "WACNN", "WACNN2"]

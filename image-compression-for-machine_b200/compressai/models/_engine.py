@@ -9,7 +9,8 @@ import ctypes as C
 import torch
 
 from compressai import _native
-from compressai._native import ACT_GELU, ACT_NONE, OUT_BF16, OUT_F32, ConvArgs, NativeError, check, lib, stream_ptr
+from compressai._native import (ACT_GELU, ACT_NONE, ACT_RSQRT, ACT_SIGMOID, ACT_SQRT, OUT_BF16, OUT_F32, RES_ADD, RES_ADD_BEFORE_ACT,
+                                RES_MUL, ConvArgs, NativeError, check, lib, stream_ptr)
 
 
 class PackedConv:
@@ -36,6 +37,28 @@ class PackedConv:
             self.bias = b.contiguous().reshape(-1).clone()
 
 
+class PackedDeconv:
+    """ConvTranspose2d(k5, s2, p2, output_padding 1) as a 3x3 convolution with 4*Cq phase-major output channels
+    and the PixelShuffle(2) store (icm_pack_deconv_weight); Cq = Cout rounded up to 16."""
+
+    __slots__ = ("w", "bias", "Cin", "Cout", "KH", "KW", "stride", "pad", "ps", "true_cout")
+
+    def __init__(self, weight, bias):
+        w = weight.detach().float().contiguous()  # [Cin, Cout, 5, 5]
+        assert w.shape[2:] == (5, 5)
+        self.Cin, self.true_cout = w.shape[0], w.shape[1]
+        cq = (self.true_cout + 15) // 16 * 16
+        cin_pad = (self.Cin + 63) // 64 * 64
+        self.Cout, self.KH, self.KW, self.stride, self.pad, self.ps = 4 * cq, 3, 3, 1, 1, 2
+        self.w = torch.empty((4 * cq, 9 * cin_pad), dtype=torch.bfloat16, device=w.device)
+        check(lib().icm_pack_deconv_weight(w.data_ptr(), self.Cin, self.true_cout, cin_pad, cq, self.w.data_ptr(), stream_ptr()),
+              "icm_pack_deconv_weight")
+        b = torch.zeros(4, cq, dtype=torch.float32, device=w.device)
+        if bias is not None:
+            b[:, : self.true_cout] = bias.detach().float()
+        self.bias = b.reshape(-1).contiguous()
+
+
 class Engine:
     def __init__(self, model):
         self.model = model
@@ -56,6 +79,11 @@ class Engine:
                 pk = PackedConv(module.weight, module.bias, module.stride[0], module.padding[0], ps)
             elif isinstance(module, torch.nn.Linear):
                 pk = PackedConv(module.weight, module.bias, 1, 0, ps)
+            elif isinstance(module, torch.nn.ConvTranspose2d):
+                pk = PackedDeconv(module.weight, module.bias)
+            elif hasattr(module, "effective"):  # GDN: 1x1 GEMM with gamma', bias beta'
+                gamma, beta = module.effective()
+                pk = PackedConv(gamma, beta, 1, 0, 0)
             else:
                 raise TypeError(type(module))
             self._packed[key] = (pk, module)  # holding the module keeps its id() from being reused
@@ -72,7 +100,7 @@ class Engine:
         return hit[0]
 
     # ---------------------------------------------------------------------------------- kernels
-    def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None):
+    def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None, res_mode=0):
         """x: bf16 [.., pitch] channels-last holding B*H*W pixels.  Returns the output tensor
         ([B*Ho*Wo(*r*r), Cout(/r^2)] unless `out` is given, then writes channels [out_offset, +Cout) of it)."""
         assert x.dtype == torch.bfloat16 and x.is_cuda
@@ -96,6 +124,8 @@ class Engine:
         a.KH, a.KW, a.stride, a.pad = pk.KH, pk.KW, pk.stride, pk.pad
         a.act, a.out_dtype, a.pixel_shuffle = act, out_dtype, pk.ps
         a.res_pitch = residual.shape[-1] if residual is not None else 0
+        a.res_dtype = OUT_BF16 if (residual is not None and residual.dtype == torch.bfloat16) else OUT_F32
+        a.res_mode = res_mode
         check(lib().icm_conv2d(C.byref(a), stream_ptr()), "icm_conv2d")
         return out
 
@@ -176,3 +206,43 @@ class Engine:
             if ps:
                 H, W = H * ps, W * ps
         return x, H, W
+
+    # ---------------------------------------------------------------------------------- WACNN pieces
+    def eltwise(self, mode, x, a=None, s=None):
+        """mode 0: x*x   1: a*s + x (bf16)   2: a*s + x (fp32)."""
+        rows, Cc = x.shape
+        out = torch.empty((rows, Cc), dtype=torch.float32 if mode == 2 else torch.bfloat16, device=x.device)
+        pa = a.shape[1] if a is not None else 0
+        ps = s.shape[1] if s is not None else 0
+        check(lib().icm_eltwise_bf16(mode, a.data_ptr() if a is not None else None, pa, s.data_ptr() if s is not None else None, ps,
+                                     x.data_ptr(), Cc, out.data_ptr(), Cc, rows, Cc, stream_ptr()), "icm_eltwise_bf16")
+        return out
+
+    def gdn(self, x, B, H, W, mod):
+        """x bf16 [B*H*W, C] -> x * rsqrt(beta' + gamma' . x^2)  (sqrt for the inverse)  (gdn.py:62-75)."""
+        sq = self.eltwise(0, x)
+        return self.conv(sq, B, H, W, self.packed(mod), act=ACT_SQRT if mod.inverse else ACT_RSQRT, residual=x, res_mode=RES_MUL)
+
+    def residual_unit(self, x, B, H, W, ru):
+        c = ru.conv
+        t = self.conv(x, B, H, W, self.packed(c[0]), act=ACT_GELU)
+        t = self.conv(t, B, H, W, self.packed(c[2]), act=ACT_GELU)
+        return self.conv(t, B, H, W, self.packed(c[4]), act=ACT_GELU, residual=x, res_mode=RES_ADD_BEFORE_ACT)
+
+    def gated_window_block(self, x, B, H, W, blk, out_f32=False):
+        """Win_noShift_Attention (layers.py:83-89): x + conv_a(x) * sigmoid(conv_b(x)); x bf16 [B*H*W, C]."""
+        Cc = x.shape[1]
+        a = x
+        for ru in blk.conv_a:
+            a = self.residual_unit(a, B, H, W, ru)
+        wba = blk.conv_b[0]
+        qkv = self.conv(x, B, H, W, self.packed(wba.attn.qkv))
+        ao = torch.empty((B * H * W, Cc), dtype=torch.bfloat16, device=x.device)
+        check(lib().icm_window_attention_wacnn(qkv.data_ptr(), ao.data_ptr(), self.f32(wba.attn.relative_position_bias_table).data_ptr(),
+                                               B, H, W, Cc, wba.num_heads, wba.window_size, wba.shift_size, stream_ptr()),
+              "icm_window_attention_wacnn")
+        b = self.conv(ao, B, H, W, self.packed(wba.attn.proj), residual=x, res_mode=RES_ADD)
+        for ru in list(blk.conv_b)[1:4]:
+            b = self.residual_unit(b, B, H, W, ru)
+        s = self.conv(b, B, H, W, self.packed(blk.conv_b[4]), act=ACT_SIGMOID)
+        return self.eltwise(2 if out_f32 else 1, x, a=a, s=s)

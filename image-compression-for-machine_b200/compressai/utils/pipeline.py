@@ -13,7 +13,7 @@ from compressai._native import check, lib
 
 
 class RoundTripPipeline:
-    def __init__(self, model, n_streams=8, part=16, conv_sm_limit=None, decoder_streams_per_cta=4):
+    def __init__(self, model, n_streams=12, part=16, conv_sm_limit=None, decoder_streams_per_cta=4):
         self.model = model
         self.decoder_streams_per_cta = int(decoder_streams_per_cta)
         # The decoder's CTAs (4 streams each, ~155 KB of shared memory) cannot share an SM with a persistent

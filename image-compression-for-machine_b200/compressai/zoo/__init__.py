@@ -5,11 +5,8 @@ from compressai.models import SymmetricalTransFormer
 
 from .pretrained import load_pretrained
 
-models = {"stf": SymmetricalTransFormer}
-try:
-    from compressai.models.cnn import WACNN
-    models["cnn"] = WACNN
-except ImportError:  # WACNN lands in a later milestone
-    pass
+from compressai.models import WACNN, WACNN2
+
+models = {"stf": SymmetricalTransFormer, "cnn": WACNN, "cnn2": WACNN2}
 
 __all__ = ["models", "load_pretrained"]

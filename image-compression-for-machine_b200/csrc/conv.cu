@@ -119,8 +119,9 @@ struct ConvParams {
     int n_tiles, total_tiles;
     int act, out_dtype, pixel_shuffle;
     long long out_pitch, res_pitch;
+    int res_dtype, res_mode; // residual operand: fp32 / bf16; added after act (0), before act (1), multiplied (2)
     const float *bias;
-    const float *residual;
+    const void *residual;
     void *out;
 };
 
@@ -150,6 +151,8 @@ __device__ __forceinline__ float apply_act(float v, int act)
     if (act == ICM_ACT_GELU) return gelu_erf(v);
     if (act == ICM_ACT_HALF_TANH) return 0.5f * tanhf(v);
     if (act == ICM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    if (act == ICM_ACT_RSQRT) return rsqrtf(v);
+    if (act == ICM_ACT_SQRT) return sqrtf(v);
     return v;
 }
 
@@ -291,6 +294,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { const float4 t = __ldg(bp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
                 }
+                float rv[16];
+                if (p.residual) { // second operand of the epilogue: fp32 (residual stream) or bf16 (activations)
+                    if (p.res_dtype == ICM_OUT_F32) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.residual) + pix * p.res_pitch + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const float4 t = __ldg(rp + j); rv[4 * j] = t.x; rv[4 * j + 1] = t.y; rv[4 * j + 2] = t.z; rv[4 * j + 3] = t.w; }
+                    } else {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.residual) + pix * p.res_pitch + n);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint4 t = __ldg(rp + j);
+                            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); rv[8 * j + 2 * k] = f.x; rv[8 * j + 2 * k + 1] = f.y; }
+                        }
+                    }
+                    if (p.res_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
                 long long off;
@@ -303,9 +327,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     off = pix * p.out_pitch + n;
                 }
                 if (p.residual) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix * p.res_pitch + n);
+                    if (p.res_mode == 0) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { const float4 t = __ldg(rp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+                        for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                    } else if (p.res_mode == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] *= rv[j];
+                    }
                 }
                 if (p.out_dtype == ICM_OUT_F32) {
                     float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
@@ -454,8 +482,10 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.act = a->act; p.out_dtype = a->out_dtype; p.pixel_shuffle = ps;
     p.out_pitch = a->out_pitch; p.res_pitch = a->res_pitch;
     p.bias = a->bias; p.residual = a->residual; p.out = a->out;
+    p.res_dtype = a->res_dtype; p.res_mode = a->res_mode;
+    ICM_CHECK_ARG(a->res_mode >= 0 && a->res_mode <= 2 && (a->res_dtype == ICM_OUT_F32 || a->res_dtype == ICM_OUT_BF16), "icm_conv2d: bad residual mode/dtype");
     ICM_CHECK_ARG(a->out_pitch % (a->out_dtype == ICM_OUT_F32 ? 4 : 8) == 0, "icm_conv2d: out_pitch=%d breaks 16-byte store alignment", a->out_pitch);
-    ICM_CHECK_ARG(!a->residual || (a->res_pitch % 4 == 0 && ((uintptr_t)a->residual & 15) == 0), "icm_conv2d: residual must be 16-byte aligned");
+    ICM_CHECK_ARG(!a->residual || (a->res_pitch % (a->res_dtype == ICM_OUT_F32 ? 4 : 8) == 0 && ((uintptr_t)a->residual & 15) == 0), "icm_conv2d: residual must be 16-byte aligned");
     ICM_CHECK_ARG(!a->bias || ((uintptr_t)a->bias & 15) == 0, "icm_conv2d: bias must be 16-byte aligned");
 
     CUtensorMap map_a, map_w;

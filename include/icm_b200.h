@@ -154,6 +154,8 @@ int icm_eb_process(int mode, icm_view z, int B, int C, int64_t P, const float *d
 #define ICM_ACT_GELU 1       /* exact erf form (nn.GELU default) */
 #define ICM_ACT_HALF_TANH 2  /* 0.5*tanh(x)  (stf.py:628) */
 #define ICM_ACT_SIGMOID 3
+#define ICM_ACT_RSQRT 4      /* GDN:  x * rsqrt(beta + gamma . x^2)  with res_mode = multiply (gdn.py:62-75) */
+#define ICM_ACT_SQRT 5       /* IGDN: x * sqrt(...) */
 #define ICM_OUT_BF16 0
 #define ICM_OUT_F32 1
 typedef struct {
@@ -161,7 +163,7 @@ typedef struct {
     const void *weight;    /* bf16 packed */
     const float *bias;     /* fp32 [Cout] or NULL */
     void *out;
-    const float *residual; /* fp32, added after activation (same indexing as out), or NULL */
+    const void *residual;  /* second epilogue operand, fp32 or bf16 (res_dtype), same indexing as out, or NULL */
     int B, H, W;           /* input spatial size */
     int Cin, in_pitch;     /* channels read per pixel (any value; zero-filled up to a multiple of 64) and row pitch */
     int Cout, out_pitch;
@@ -169,6 +171,8 @@ typedef struct {
     int act, out_dtype;
     int pixel_shuffle;     /* 0 or r: output written as PixelShuffle(r) of the conv result */
     int res_pitch;
+    int res_dtype;         /* ICM_OUT_F32 / ICM_OUT_BF16 */
+    int res_mode;          /* 0: out = act(acc) + res   1: out = act(acc + res)   2: out = act(acc) * res */
 } icm_conv_args;
 int icm_conv2d(const icm_conv_args *a, void *stream);
 /* Cap on the SMs icm_conv2d occupies (0 = all), for overlap with the rANS coders on another stream. */
@@ -202,6 +206,27 @@ int icm_patch_embed(const float *d_img, const float *d_w, const float *d_b, cons
  *     (stf.py:466,784). */
 int icm_final_conv(const void *d_in_bf16, const float *d_w, const float *d_b, float *d_img, int B, int H,
                    int W, int C, int clamp01, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T11  WACNN ("cnn" / "cnn2" codec) pieces; the convolutions themselves go through icm_conv2d.
+ *
+ * NCHW fp32 image <-> channels-last bf16 (`pitch` channels, the extra ones zero / ignored); the output
+ * conversion optionally clamps to [0,1] (cnn.py:331). */
+int icm_image_to_nhwc(const float *d_img, void *d_out_bf16, int B, int C, int H, int W, int pitch, void *stream);
+int icm_nhwc_to_image(const void *d_in_bf16, float *d_img, int B, int C, int H, int W, int pitch, int clamp01, void *stream);
+/* mode 0: out = x*x (the GDN operand, gdn.py:68); mode 1: out = a*s + x (gated attention output, layers.py:87-89);
+ * mode 2: the same written as fp32 (the latent y);
+ * bf16 [rows, C] blocks with row pitches in elements. */
+int icm_eltwise_bf16(int mode, const void *d_a, int64_t pitch_a, const void *d_s, int64_t pitch_s, const void *d_x,
+                     int64_t pitch_x, void *d_out, int64_t pitch_out, int64_t rows, int C, void *stream);
+/* WindowAttention core of WinBasedAttention (win_attention.py:90-207): window 8 / head_dim 24 and window 4 /
+ * head_dim 40, optional cyclic shift + region mask, no padding; qkv bf16 [B,H,W,3C] -> bf16 [B,H,W,C]. */
+int icm_window_attention_wacnn(const void *d_qkv, void *d_out, const float *d_bias_table, int B, int H, int W, int C,
+                               int heads, int window, int shift, void *stream);
+/* ConvTranspose2d(k5, s2, p2, output_padding 1) weight [Cin][Cout][5][5] -> the packed weight of an equivalent
+ * 3x3 convolution with 4*Cq phase-major output channels, to be run by icm_conv2d with pixel_shuffle = 2
+ * (models/utils.py:124-132). */
+int icm_pack_deconv_weight(const float *d_w_iohw, int Cin, int Cout, int Cin_pad, int Cq, void *d_out_bf16, void *stream);
 
 #ifdef __cplusplus
 }
