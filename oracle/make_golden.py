@@ -1,6 +1,7 @@
 """Generate tests/golden/* from the REFERENCE ITSELF (run in the build container only).
 
     python -m oracle.make_golden          # from the repo root; needs /root/reference
+    python -m oracle.make_golden cnn      # only tests/golden/cnn_small.npz (WACNN, 256x256 = BASELINE configs[0])
 
 Sources of truth used here:
   * the reference's shipped native binaries, executed through oracle/refbin.py (rANS, pmf->cdf);
@@ -202,5 +203,63 @@ def main():
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
 
+def cnn_golden():
+    """Model-level fixture for WACNN (cnn.py) at 1x3x256x256, seeded stress weights."""
+    h = refshim.install("binary")
+    cnn = h["cnn"]
+    torch.manual_seed(0)
+    m = cnn.WACNN().eval()
+    sd = weights.seeded_state_dict(m.state_dict(), seed=0, stress=True)
+    m.load_state_dict(sd)
+    m.update(force=True)
+    x = weights.seeded_image((1, 3, 256, 256), seed=0)
+    rec = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            rec.setdefault(name, []).append(out.detach().clone())
+        return f
+
+    hs = []
+    for i in range(10):
+        hs.append(m.cc_mean_transforms[i].register_forward_hook(hook("mu")))
+        hs.append(m.cc_scale_transforms[i].register_forward_hook(hook("scale")))
+    for name in ("g_a", "h_a", "h_mean_s", "h_scale_s"):
+        hs.append(getattr(m, name).register_forward_hook(hook(name)))
+    hs.append(m.g_a[1].register_forward_hook(hook("gdn0")))
+    hs.append(m.g_a[4].register_forward_hook(hook("win0")))
+    with torch.no_grad():
+        out = m(x)
+        fwd = {k: [t.clone() for t in v] for k, v in rec.items()}
+        rec.clear()
+        c = m.compress(x)
+        d = m.decompress(c["strings"], c["shape"])
+    for hh in hs:
+        hh.remove()
+    assert torch.equal(d["x_hat"], out["x_hat"].clamp(0, 1))
+    y = fwd["g_a"][0]
+    mu = torch.cat(fwd["mu"], 1)
+    sc = torch.cat(fwd["scale"], 1)
+    sym = torch.round(y - mu).int()
+    idx = m.gaussian_conditional.build_indexes(sc)
+    print("cnn_small: y-string", len(c["strings"][0][0]), "B z-string", len(c["strings"][1][0]), "B; distinct idx", idx.unique().numel(),
+          "max|sym|", int(sym.abs().max()), "psnr", float(-10 * torch.log10(torch.mean((x - d['x_hat']) ** 2))))
+    np.savez_compressed(
+        os.path.join(GOLD, "cnn_small.npz"),
+        y=y.numpy(), z=fwd["h_a"][0].numpy(), latent_means=fwd["h_mean_s"][0].numpy(), latent_scales=fwd["h_scale_s"][0].numpy(),
+        gdn0=fwd["gdn0"][0][:, :, ::4, ::4].numpy(), win0=fwd["win0"][0][:, :, ::2, ::2].numpy(),
+        mu=mu.numpy(), scale=sc.numpy(), symbols=sym.numpy().astype(np.int32), indexes=idx.numpy().astype(np.uint8),
+        x_hat=out["x_hat"].numpy(), y_lik=out["likelihoods"]["y"].numpy(), z_lik=out["likelihoods"]["z"].numpy(),
+        y_string=np.frombuffer(c["strings"][0][0], np.uint8), z_string=np.frombuffer(c["strings"][1][0], np.uint8),
+        eb_cdf=m.entropy_bottleneck._quantized_cdf.numpy(), eb_len=m.entropy_bottleneck._cdf_length.numpy(),
+        eb_off=m.entropy_bottleneck._offset.numpy(),
+    )
+    print("cnn_small.npz", os.path.getsize(os.path.join(GOLD, "cnn_small.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["cnn"]:
+        cnn_golden()
+    else:
+        main()
+        cnn_golden()

@@ -171,17 +171,17 @@ def eb_params(sd):
     return _sub(sd, "entropy_bottleneck.")
 
 
-def slice_loop(sd, y, latent_means, latent_scales, mode, decoder=None, tables=None):
+def slice_loop(sd, y, latent_means, latent_scales, mode, decoder=None, tables=None, num_slices=NUM_SLICES, max_support=MAX_SUPPORT):
     """:607-631 (forward), :703-726 (compress), :754-776 (decompress).
 
     mode "forward": returns (y_hat, y_likelihoods); "compress": returns (y_hat, symbols, indexes) with
     symbols/indexes lists per slice [B,32,h,w]; "decompress": y is None, symbols come from `decoder`.
     """
     table = entropy.scale_table()
-    y_slices = y.chunk(NUM_SLICES, 1) if y is not None else [None] * NUM_SLICES
+    y_slices = y.chunk(num_slices, 1) if y is not None else [None] * num_slices
     hats, liks, syms, idxs = [], [], [], []
-    for i in range(NUM_SLICES):
-        support = hats[:MAX_SUPPORT]
+    for i in range(num_slices):
+        support = hats[:max_support]
         mean_support = torch.cat([latent_means] + support, 1)
         mu = conv_stack(sd, f"cc_mean_transforms.{i}", mean_support)
         scale_support = torch.cat([latent_scales] + support, 1)

@@ -72,6 +72,9 @@ def seeded_state_dict(template, seed=0, stress=True):
         k = "layers.2.downsample.reduction.weight"
         if k in out:
             out[k] = out[k] * 8.0
+        k = "g_a.7.weight"  # WACNN: the last analysis convolution sets the latent's magnitude
+        if k in out:
+            out[k] = out[k] * 48.0
         ramp = torch.exp(torch.linspace(math.log(0.05), math.log(30.0), 32))
         for name in out:
             if name.startswith("cc_scale_transforms.") and name.endswith(".8.bias"):

@@ -11,8 +11,9 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
-from oracle import coder, entropy, stf_ref, weights
+from oracle import cnn_ref, coder, entropy, stf_ref, weights
 from oracle.make_golden import seeded_stream
 
 
@@ -151,4 +152,35 @@ def test_stf_restatement_matches_reference_model(golden_dir):
     assert c["strings"][1][0] == g["z_string"].tobytes()
     assert c["strings"][0][0] == g["y_string"].tobytes()
     d = stf_ref.decompress(sd, c["strings"], c["shape"], eb_tab=eb_tab)
+    assert torch.allclose(d["x_hat"], torch.from_numpy(g["x_hat"]).clamp(0, 1), rtol=1e-3, atol=1e-4)
+
+
+def test_wacnn_restatement_matches_reference_model(golden_dir):
+    """oracle/cnn_ref.py (functional fp32) vs the reference WACNN nn.Module run in make_golden.py (256x256, configs[0])."""
+    g = np.load(os.path.join(golden_dir, "cnn_small.npz"))
+    sd = weights.seeded_state_dict(cnn_ref.template_state_dict(), seed=0, stress=True)
+    x = weights.seeded_image((1, 3, 256, 256), seed=0)
+    # intermediate activations: first GDN and first gated window block of g_a (stored subsampled)
+    t = F.conv2d(x, sd["g_a.0.weight"], sd["g_a.0.bias"], stride=2, padding=2)
+    t = cnn_ref.gdn(t, sd, "g_a.1", False)
+    assert torch.allclose(t[:, :, ::4, ::4], torch.from_numpy(g["gdn0"]), rtol=1e-4, atol=1e-5)
+    out = cnn_ref.forward(sd, x)
+    tol = dict(rtol=1e-4, atol=2e-5)
+    assert torch.allclose(out["y"], torch.from_numpy(g["y"]), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(out["z"], torch.from_numpy(g["z"]), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(out["x_hat"], torch.from_numpy(g["x_hat"]), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(out["likelihoods"]["y"], torch.from_numpy(g["y_lik"]), rtol=1e-3, atol=1e-9)
+    assert torch.allclose(out["likelihoods"]["z"], torch.from_numpy(g["z_lik"]), rtol=1e-3, atol=1e-9)
+    eb_tab = entropy.eb_tables(stf_ref.eb_params(sd))
+    assert np.array_equal(eb_tab[0], g["eb_cdf"]) and np.array_equal(eb_tab[1], g["eb_len"]) and np.array_equal(eb_tab[2], g["eb_off"])
+    y, mu, sc = (torch.from_numpy(g[k]) for k in ("y", "mu", "scale"))
+    sym = entropy.quantize_symbols(y, mu)
+    idx = entropy.build_indexes(sc, entropy.scale_table())
+    assert np.array_equal(sym.numpy(), g["symbols"]) and np.array_equal(idx.numpy(), g["indexes"].astype(np.int32))
+    order = lambda t: np.concatenate([c.reshape(-1).numpy() for c in t[0:1].chunk(10, 1)])
+    assert coder.rans_encode(order(sym), order(idx), *entropy.gc_tables()) == g["y_string"].tobytes()
+    c = cnn_ref.compress(sd, x, eb_tab=eb_tab)
+    assert c["strings"][1][0] == g["z_string"].tobytes()
+    assert c["strings"][0][0] == g["y_string"].tobytes()
+    d = cnn_ref.decompress(sd, c["strings"], c["shape"], eb_tab=eb_tab)
     assert torch.allclose(d["x_hat"], torch.from_numpy(g["x_hat"]).clamp(0, 1), rtol=1e-3, atol=1e-4)
