@@ -41,13 +41,13 @@ WEIGHTS = {"default": "PyTorch default init under torch.manual_seed(0) (the refe
            "stress": "default init + the survey's rate-raising tweak (SURVEY.md 8d: many CDF tables, ~26% escape symbols)"}
 
 
-def make_model(device, weights="default"):
-    """Reference-architecture STF, random weights (no checkpoint ships with the reference)."""
+def make_model(device, weights="default", arch="stf"):
+    """Reference-architecture STF (or WACNN), random weights (no checkpoint ships with the reference)."""
     from compressai.zoo import models
 
     torch.manual_seed(0)
-    m = models["stf"]()
-    if weights == "stress":
+    m = models[arch]()
+    if weights == "stress" and arch == "stf":
         with torch.no_grad():
             m.layers[2].downsample.reduction.weight.mul_(8.0)
             ramp = torch.exp(torch.linspace(math.log(0.05), math.log(30.0), 32))

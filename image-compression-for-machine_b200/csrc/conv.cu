@@ -146,14 +146,35 @@ __device__ __forceinline__ float gelu_erf(float v)
     return fmaf(fabsf(h), erf_abs, h); // v * erf(v / sqrt 2) is even in v
 }
 
-__device__ __forceinline__ float apply_act(float v, int act)
+// The activation switch sits OUTSIDE the 16-element loop (one uniform branch per chunk): with it inside, the
+// unrolled epilogue carried every activation's code and a branch chain per element (~32 instructions per
+// output; the stage-0 GELU linear was issue-bound at a fifth of the HBM roofline).
+__device__ __forceinline__ void apply_act16(float (&v)[16], int act)
 {
-    if (act == ICM_ACT_GELU) return gelu_erf(v);
-    if (act == ICM_ACT_HALF_TANH) return 0.5f * tanhf(v);
-    if (act == ICM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-    if (act == ICM_ACT_RSQRT) return rsqrtf(v);
-    if (act == ICM_ACT_SQRT) return sqrtf(v);
-    return v;
+    switch (act) {
+    case ICM_ACT_GELU:
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        break;
+    case ICM_ACT_HALF_TANH:
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.5f * tanhf(v[j]);
+        break;
+    case ICM_ACT_SIGMOID:
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[j]));
+        break;
+    case ICM_ACT_RSQRT:
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v[j])); v[j] = y; }
+        break;
+    case ICM_ACT_SQRT:
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v[j])); v[j] = y; }
+        break;
+    default:
+        break;
+    }
 }
 
 constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
@@ -315,8 +336,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int j = 0; j < 16; ++j) v[j] += rv[j];
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+                apply_act16(v, p.act);
                 long long off;
                 if (p.pixel_shuffle) {
                     const int rr = p.pixel_shuffle;
