@@ -16,6 +16,12 @@ configs[2] on each GPU; the batch shards across GPUs with no collective, weak sc
                 reference's path) on this box's host cores, on a bounded sample of the same workload
   --impl reference   times only that CPU path (rank 0), same metric / config, and prints its own line.
 """
+import os as _os
+
+# one hardware work queue per pipeline stream: with the default of 8, streams alias and a 5 ms rANS step of one
+# job falsely serialises the convolutions of another (measured: 16 streams ran at half the speed of 8)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse
 import json
 import math
@@ -63,33 +69,59 @@ def make_images(batch, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md clocks line), read in-process through
+    NVML every 100 ms.  (A polling `nvidia-smi -lms` child process was measurably intrusive: the pipelined step
+    time became bimodal, 120 vs 175 ms, with it running.)  Falls back to one nvidia-smi query per sample."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.1):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.period, self.rows, self._stop_ev = index, period, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:  # noqa: BLE001
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            return mhz, self.max_mhz, [name for name, bit in self.NAMES if mask & bit]
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
+        c = [v.strip() for v in out.split(",")]
+        return float(c[0]), float(c[1]), [name for (name, _), v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")]
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:  # noqa: BLE001
-            pass
+        while not self._stop_ev.is_set():
+            try:
+                self.rows.append(self._sample())
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_ev.wait(self.period if self.nvml is not None else 0.5)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        self.join(timeout=2)
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        self._stop_ev.set()
+        self.join(timeout=3)
+        sm = sorted(r[0] for r in self.rows)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[1] for r in self.rows), default=None),
+                "reasons": sorted({n for r in self.rows for n in r[2]}), "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def pipe_capacity_bytes(B):
@@ -124,7 +156,7 @@ def cpu_baseline(model_sd, n_images, steps=1, warmup=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -134,6 +166,8 @@ def main():
     ap.add_argument("--streams", type=int, default=12, help="CUDA streams of the codec pipeline")
     ap.add_argument("--part", type=int, default=16, help="images per pipeline job")
     ap.add_argument("--dec-per-cta", type=int, default=4, help="rANS decoder streams per CTA in the pipeline (1, 2, 4)")
+    ap.add_argument("--lag", type=int, default=6, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag")
+    ap.add_argument("--chains", type=int, default=2, help="pipeline: jobs allowed in a throughput-bound phase at once (0 = unordered)")
     ap.add_argument("--conv-sms", type=int, default=-1, help="cap on SMs used by the conv kernel (0 = all, -1 = automatic)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -142,7 +176,8 @@ def main():
     workload = f"stf 3x{H_IMG}x{W_IMG}, {args.batch} images per GPU per step (BASELINE.json configs[2]; batch sharded, no collective)"
     config = {"workload": workload, "images_per_gpu": args.batch, "height": H_IMG, "width": W_IMG,
               "weights": WEIGHTS[args.weights], "l2": "inputs larger than L2 (302 MB per batch at B=64)",
-              "pipeline": f"{args.streams} CUDA streams x jobs of {args.part} images (compress -> decompress per job), K steps in flight"}
+              "pipeline": f"{args.streams} CUDA streams x jobs of {args.part} images (compress -> decompress per job), K steps in flight; "
+                          f"transform phases ordered in {args.chains} event chains, synthesis lagging {args.lag} jobs"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -183,7 +218,7 @@ def main():
     from compressai.utils.pipeline import RoundTripPipeline
 
     pipe = RoundTripPipeline(model, n_streams=args.streams, part=min(args.part, B), conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
-                             decoder_streams_per_cta=args.dec_per_cta)
+                             decoder_streams_per_cta=args.dec_per_cta, lag=args.lag, chains=args.chains)
     out_bufs = [out_host, torch.empty_like(out_host).pin_memory()] if not args.no_e2e else []
 
     def run_device(steps):
@@ -216,7 +251,11 @@ def main():
         barrier()
         return ms, launches, r
 
-    run_device(max(args.warmup, 3))
+    # at least 3 untimed steps, and enough of them for every pipeline stream to have run a job (each stream owns a
+    # slice of the caching allocator and a decoder pair: their first use must not fall into the timed region)
+    jobs_per_step = -(-B // min(args.part, B))
+    warm_steps = max(args.warmup, 3, -(-args.streams // jobs_per_step))
+    run_device(warm_steps)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -246,19 +285,31 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         model.micro_batches = 1
+        torch.cuda.synchronize()
+        # cudaProfilerStart/Stop bracket exactly this step: `ncu --profile-from-start off ... python bench.py` then
+        # lists the launches the roofline below is computed from (profiles/README.md), not the pipelined warm-up.
+        torch.cuda.cudart().cudaProfilerStart()
         with _native.Profile() as prof:  # plain API, one stream: clean per-kernel times
             c = model.compress(x_dev, device_strings=True)
             model.decompress(c["strings"], c["shape"])
             summ = prof.summary()
+        torch.cuda.cudart().cudaProfilerStop()
         total_ms = sum(v[1] for v in summ.values())
         families = {k: {"calls": v[0], "ms": round(v[1], 3), "share": round(v[1] / total_ms, 4)} for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
         calls, conv_ms, conv_flops = summ.get("icm_conv2d", (0, 0.0, 0.0))
         dec_ms = summ.get("icm_rans_decoder_step", (0, 0.0, 0.0))[1]
         enc_ms = summ.get("icm_rans_encode_batch", (0, 0.0, 0.0))[1]
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per conv launch from the committed `ncu --set full` capture of this workload (B = 64 only)
+            tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["conv_igemm_kernel"]
+            if tj.get("images_per_step") == B and tj.get("workload") == "stf":
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:  # noqa: BLE001
+            pass
         ach = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms else 0.0
         roofline = {"kernel": "conv_igemm_kernel (icm_conv2d: all convolutions and linears)", "bound": "tensor", "achieved": round(ach, 2),
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": None,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
                     "launches_per_step": calls, "avg_launch_us": round(conv_ms * 1e3 / max(calls, 1), 2),
                     "algorithmic_flops_per_step": conv_flops, "share_of_step": round(conv_ms / total_ms, 4),
@@ -272,7 +323,7 @@ def main():
                "sample": f"2 images (3x768x512) compress+decompress once ({dt:.1f} s), oracle/stf_ref.py fp32 + oracle/rans_oracle.c"}
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm_steps,
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 operands / fp32 accumulate (transforms); fp32 (entropy models); u64 (rANS)", "data": "synthetic",
             "config": config, "clocks": clocks,

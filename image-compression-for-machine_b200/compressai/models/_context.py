@@ -188,10 +188,13 @@ class ChannelContextCodec(CompressionModel):
             t.record_stream(torch.cuda.current_stream())
         return t
 
-    def _compress_part(self, x):
-        """compress() of one micro-batch, fully asynchronous: device-resident streams."""
+    def _compress_part(self, x, phase=None):
+        """compress() of one micro-batch, fully asynchronous: device-resident streams.  `phase("begin"/"end")`
+        brackets the throughput-bound part (transforms + slice loop); the rANS encoders run after "end"."""
         eb = self.entropy_bottleneck
         B = x.shape[0]
+        if phase:
+            phase("begin")
         y, h, w = self._analysis(x)
         z, zh, zw = self._hyper_analysis(y, B, h, w)
         Pz, Zc = zh * zw, self.hyper_channels
@@ -203,6 +206,8 @@ class ChannelContextCodec(CompressionModel):
               "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
         _, sym, idx = self._slice_loop("compress", B, h, w, mean_sup, scale_sup, y=y)
+        if phase:
+            phase("end")
         z_str = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device="async")
         y_str = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device="async")
         return {"y": y_str, "z": z_str, "shape": (zh, zw), "retry": (sym, idx, z_sym, z_idx)}
@@ -233,6 +238,11 @@ class ChannelContextCodec(CompressionModel):
         return {"strings": [y_strings, z_strings], "shape": shape}
 
     def _decompress_part(self, y_str, z_str, B, zh, zw, on_device, decoders=None):
+        y_hat, decs = self._decode_part(y_str, z_str, B, zh, zw, on_device, decoders)
+        return self._synthesis(y_hat, B, 4 * zh, 4 * zw, clamp=True), decs
+
+    def _decode_part(self, y_str, z_str, B, zh, zw, on_device, decoders=None):
+        """The latency-bound half of decompress(): z decode, hyper-synthesis, the slice loop around the y decoder."""
         eb = self.entropy_bottleneck
         dev = eb.quantiles.device
         Pz, Zc = zh * zw, self.hyper_channels
@@ -248,8 +258,7 @@ class ChannelContextCodec(CompressionModel):
         ydec = decoders[1] if decoders is not None else ans.acquire_decoder(B)
         ydec.set_streams_device(*y_str) if on_device else ydec.set_streams(y_str)
         y_hat, _, _ = self._slice_loop("decompress", B, h, w, mean_sup, scale_sup, decoder=ydec)
-        x_hat = self._synthesis(y_hat, B, h, w, clamp=True)
-        return x_hat, (zdec, ydec)
+        return y_hat, (zdec, ydec)
 
     @torch.no_grad()
     def decompress(self, strings, shape):

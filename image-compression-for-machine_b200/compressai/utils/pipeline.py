@@ -7,23 +7,45 @@ same and of following batches are spread round-robin over the pool, and the GPU 
 job with the convolutions of the others.  The per-image results are bit-identical to model.compress /
 model.decompress on the whole batch (every kernel is batch-invariant).
 """
+import os
+import warnings
+
 import torch
 
 from compressai._native import check, lib
 
+# The pipeline needs one hardware work queue per stream; CUDA's default is 8 and streams beyond that alias, which
+# serialises a 5 ms rANS step of one job with the convolutions of another.  The variable is read when the CUDA
+# context is created, so it only helps if this module is imported before the first CUDA call.
+if "CUDA_DEVICE_MAX_CONNECTIONS" not in os.environ:
+    if torch.cuda.is_initialized():
+        warnings.warn("compressai.utils.pipeline imported after CUDA initialisation: set CUDA_DEVICE_MAX_CONNECTIONS=32 "
+                      "in the environment, or use at most 8 pipeline streams", stacklevel=2)
+    else:
+        os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
+
 
 class RoundTripPipeline:
-    def __init__(self, model, n_streams=12, part=16, conv_sm_limit=None, decoder_streams_per_cta=4):
+    """lag / chains: the throughput-bound phases (compress transforms "C", synthesis "S") of all jobs are ordered
+    into `chains` token chains C_t, S_{t-lag}, C_{t+1}, S_{t-lag+1}, ... with CUDA events, so that at most `chains`
+    jobs compete for the tensor cores at any time while the rANS phases (encode after C, the decode loop before S) of
+    up to `lag` other jobs run beside them.  Without the chain all jobs start in lockstep, reach their coders
+    together and leave the GPU idle (measured run-to-run spread 400-530 images/s)."""
+
+    def __init__(self, model, n_streams=12, part=16, conv_sm_limit=None, decoder_streams_per_cta=4, lag=6, chains=2):
         self.model = model
         self.decoder_streams_per_cta = int(decoder_streams_per_cta)
-        # The decoder's CTAs (4 streams each, ~155 KB of shared memory) cannot share an SM with a persistent
-        # conv CTA (~200 KB); the conv grid leaves them room.  None = 148 - streams * ceil(part / 4).
+        # The decoder's CTAs (~155 KB of shared memory) cannot share an SM with a persistent conv CTA (~200 KB); the
+        # conv grid leaves them room.  None = 148 - (jobs in their decode loop) * ceil(part / streams per CTA).
         self.conv_sm_limit = conv_sm_limit
         self.n_streams = int(n_streams)
         self.part = int(part)
+        self.lag = max(0, min(int(lag), self.n_streams - 1))
+        self.chains = max(0, int(chains))
         self._streams = None
         self._decoders = {}
         self._pinned = {}
+        self._tokens = {}
 
     def _setup(self, device):
         if self._streams is None or self._streams[0].device != device:
@@ -45,6 +67,23 @@ class RoundTripPipeline:
             self._pinned[key] = t
         return t
 
+    def _phase(self, chain):
+        """begin: wait for the chain's token; end: pass it on."""
+        if self.chains == 0:
+            return None
+
+        def hook(what):
+            st = torch.cuda.current_stream()
+            if what == "begin":
+                ev = self._tokens.get(chain)
+                if ev is not None:
+                    st.wait_event(ev)
+            else:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self._tokens[chain] = ev
+        return hook
+
     @torch.no_grad()
     def roundtrip(self, batches, host_io=False, out_host=None):
         """compress + decompress every batch of `batches` ([B,3,H,W] CUDA tensors, or pinned host tensors with
@@ -58,42 +97,64 @@ class RoundTripPipeline:
         limit = self.conv_sm_limit
         if limit is None:
             per = max(1, self.decoder_streams_per_cta)
-            limit = max(sms // 2, sms - self.n_streams * ((self.part + per - 1) // per))
+            decoding = self.n_streams if self.chains == 0 else min(self.n_streams, self.lag + 1)
+            limit = max(sms // 2, sms - decoding * ((self.part + per - 1) // per))
         check(lib().icm_set_conv_sm_limit(int(limit)), "icm_set_conv_sm_limit")
         check(lib().icm_set_decoder_streams_per_cta(self.decoder_streams_per_cta), "icm_set_decoder_streams_per_cta")
         for st in self._streams:
             st.wait_stream(cur)
-        results, pending, job = [], [], 0
+        self._tokens = {}
+        jobs = []
+        for bi, x in enumerate(batches):
+            m._check_input(x if not host_io else x[:1].to(dev))
+            for lo in range(0, x.shape[0], self.part):
+                jobs.append((bi, lo, min(x.shape[0], lo + self.part)))
+        results = [[] for _ in batches]
+        pending, decoded = [], {}
+        lag = self.lag if self.chains else 0
+
+        def front(t):  # C phase + encoders + decode loop of job t
+            bi, lo, hi = jobs[t]
+            slot = t % self.n_streams
+            x = batches[bi]
+            with torch.cuda.stream(self._streams[slot]):
+                xd = x[lo:hi].to(dev, non_blocking=True) if host_io else x[lo:hi]
+                c = m._compress_part(xd, phase=self._phase(t % self.chains) if self.chains else None)
+                zh, zw = c["shape"]
+                y_str, z_str = c["y"], c["z"]
+                if host_io:  # streams leave for the host and come back, like bytes handed to a decoder
+                    hy = self._pin(("y", bi, lo), y_str[0].shape, torch.uint8)
+                    hz = self._pin(("z", bi, lo), z_str[0].shape, torch.uint8)
+                    hsy = self._pin(("sy", bi, lo), y_str[1].shape, torch.int32)
+                    hsz = self._pin(("sz", bi, lo), z_str[1].shape, torch.int32)
+                    hy.copy_(y_str[0], non_blocking=True); hz.copy_(z_str[0], non_blocking=True)
+                    hsy.copy_(y_str[1], non_blocking=True); hsz.copy_(z_str[1], non_blocking=True)
+                    y_str = (hy.to(dev, non_blocking=True), hsy.to(dev, non_blocking=True))
+                    z_str = (hz.to(dev, non_blocking=True), hsz.to(dev, non_blocking=True))
+                    pending.append((bi, lo, hi, hy, hsy, hz, hsz))
+                y_hat, _ = m._decode_part(y_str, z_str, hi - lo, zh, zw, True, decoders=self._decoder_pair(slot, hi - lo))
+                decoded[t] = (y_hat, zh, zw)
+
+        def back(t):  # S phase of job t
+            bi, lo, hi = jobs[t]
+            y_hat, zh, zw = decoded.pop(t)
+            with torch.cuda.stream(self._streams[t % self.n_streams]):
+                hook = self._phase(t % self.chains) if self.chains else None
+                if hook:
+                    hook("begin")
+                x_hat = m._synthesis(y_hat, hi - lo, 4 * zh, 4 * zw, clamp=True)
+                if hook:
+                    hook("end")
+                if out_host is not None:
+                    out_host[bi][lo:hi].copy_(x_hat, non_blocking=True)
+                results[bi].append(x_hat)
+
         try:
-            for bi, x in enumerate(batches):
-                B = x.shape[0]
-                m._check_input(x if not host_io else x[:1].to(dev))
-                parts = []
-                for lo in range(0, B, self.part):
-                    hi = min(B, lo + self.part)
-                    slot = job % self.n_streams
-                    st = self._streams[slot]
-                    job += 1
-                    with torch.cuda.stream(st):
-                        xd = x[lo:hi].to(dev, non_blocking=True) if host_io else x[lo:hi]
-                        c = m._compress_part(xd)
-                        zh, zw = c["shape"]
-                        y_str, z_str = c["y"], c["z"]
-                        if host_io:  # streams leave for the host and come back, like bytes handed to a decoder
-                            hy = self._pin(("y", bi, lo), y_str[0].shape, torch.uint8)
-                            hz = self._pin(("z", bi, lo), z_str[0].shape, torch.uint8)
-                            hsy = self._pin(("sy", bi, lo), y_str[1].shape, torch.int32)
-                            hsz = self._pin(("sz", bi, lo), z_str[1].shape, torch.int32)
-                            hy.copy_(y_str[0], non_blocking=True); hz.copy_(z_str[0], non_blocking=True)
-                            hsy.copy_(y_str[1], non_blocking=True); hsz.copy_(z_str[1], non_blocking=True)
-                            y_str = (hy.to(dev, non_blocking=True), hsy.to(dev, non_blocking=True))
-                            z_str = (hz.to(dev, non_blocking=True), hsz.to(dev, non_blocking=True))
-                            pending.append((bi, lo, hi, hy, hsy, hz, hsz))
-                        x_hat, _ = m._decompress_part(y_str, z_str, hi - lo, zh, zw, True, decoders=self._decoder_pair(slot, hi - lo))
-                        if out_host is not None:
-                            out_host[bi][lo:hi].copy_(x_hat, non_blocking=True)
-                        parts.append(x_hat)
-                results.append(parts)
+            for t in range(len(jobs) + lag):
+                if t < len(jobs):
+                    front(t)
+                if t - lag >= 0:
+                    back(t - lag)
             for st in self._streams:
                 cur.wait_stream(st)
         finally:

@@ -409,7 +409,8 @@ __device__ __noinline__ SlowRet dec_slow(DecState d, DecCtx c, SlowArgs a, uint3
     return r;
 }
 
-constexpr int kDecWarps = 4; // max streams per CTA: one per SM sub-partition, sharing the tables in shared memory
+constexpr int kDecWarps = 16; // max streams per CTA: they share one copy of the tables in shared memory; each warp is
+                              // latency-bound (one instruction every ~4 cycles), so four per scheduler still interleave
 
 __global__ void __launch_bounds__(kDecWarps * 32) rans_decode_kernel(TablesDev T, int n_streams, const uint32_t *__restrict__ words,
                                                          const int64_t *__restrict__ word_off,
@@ -754,13 +755,13 @@ extern "C" int icm_rans_decoder_set_streams_device(icm_rans_decoder *d, const ui
     return ICM_OK;
 }
 
-// Streams per decoder CTA (1, 2 or 4; 0 = automatic).  One stream per CTA is fastest per stream (a whole SM to
+// Streams per decoder CTA (1, 2, 4, 8 or 16; 0 = automatic).  One stream per CTA is fastest per stream (a whole SM to
 // itself); more streams per CTA share one copy of the tables in shared memory and leave more SMs to other
 // kernels -- what a pipeline that overlaps the decoder with the convolutions wants.
 static thread_local int g_dec_warps = 0;
 extern "C" int icm_set_decoder_streams_per_cta(int n)
 {
-    ICM_CHECK_ARG(n == 0 || n == 1 || n == 2 || n == 4, "icm_set_decoder_streams_per_cta: %d is not 0, 1, 2 or 4", n);
+    ICM_CHECK_ARG(n == 0 || n == 1 || n == 2 || n == 4 || n == 8 || n == 16, "icm_set_decoder_streams_per_cta: %d is not 0, 1, 2, 4, 8 or 16", n);
     g_dec_warps = n;
     return ICM_OK;
 }

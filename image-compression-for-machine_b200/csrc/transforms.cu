@@ -8,63 +8,80 @@
 namespace icm {
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over C (eps 1e-5), one warp per output row.  gather: row (b,h2,w2) is the concatenation of the
-// four tokens (2h2+dh, 2w2+dw) in the order (0,0),(1,0),(0,1),(1,1)  (stf.py:225-229), zero beyond H/W.
-template <typename OutT, int MAXV>
+// LayerNorm over C (eps 1e-5).  LPR lanes share one row, every lane holds NQ float4 (LPR * NQ * 4 >= C), so a warp
+// normalises 32 / LPR rows at once with 16-byte loads: at C = 48 that is 8 rows and 48 bytes in flight per lane
+// (the one-row-per-warp version had 8 and ran at a quarter of the HBM roofline).
+// gather: row (b,h2,w2) is the concatenation of the four tokens (2h2+dh, 2w2+dw) in the order (0,0),(1,0),(0,1),(1,1)
+// (stf.py:225-229), zero beyond H/W; C/4 is a multiple of 4, so a float4 never straddles two source tokens.
+template <typename OutT, int LPR, int NQ>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, OutT *__restrict__ out,
                                                         long long rows, int C, int gather, int H, int W)
 {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    float v[MAXV]; // MAXV * 32 >= C
-
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool row_ok = row < rows;
     const int Cs = gather ? C / 4 : C; // channels per source token
     int H2 = 0, W2 = 0, b = 0, h2 = 0, w2 = 0;
     if (gather) {
         H2 = (H + 1) / 2; W2 = (W + 1) / 2;
-        long long t = row;
+        long long t = row_ok ? row : 0;
         w2 = (int)(t % W2); t /= W2;
         h2 = (int)(t % H2); b = (int)(t / H2);
     }
+    float4 v[NQ];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int c = lane + 32 * i;
-        float x = 0.f;
-        if (c < C) {
+    for (int i = 0; i < NQ; ++i) {
+        const int c = 4 * (sub + LPR * i);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && c < C) {
             if (gather) {
                 const int k = c / Cs, cc = c - k * Cs;
                 const int hh = 2 * h2 + (k & 1), ww = 2 * w2 + (k >> 1);
-                if (hh < H && ww < W) x = in[(((long long)b * H + hh) * W + ww) * Cs + cc];
+                if (hh < H && ww < W) x = __ldg(reinterpret_cast<const float4 *>(in + (((long long)b * H + hh) * W + ww) * Cs + cc));
             } else {
-                x = in[row * C + c];
+                x = __ldg(reinterpret_cast<const float4 *>(in + row * C + c));
             }
         }
         v[i] = x;
-        sum += x;
+        sum += (x.x + x.y) + (x.z + x.w);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / (float)C;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int c = lane + 32 * i;
-        const float d = (c < C) ? v[i] - mean : 0.f;
-        sq += d * d;
+    for (int i = 0; i < NQ; ++i) {
+        if (4 * (sub + LPR * i) < C) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + bb * bb) + (cc * cc + d * d);
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / (float)C + 1e-5f);
+    if (!row_ok) return;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int c = lane + 32 * i;
+    for (int i = 0; i < NQ; ++i) {
+        const int c = 4 * (sub + LPR * i);
         if (c < C) {
-            const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
-            if constexpr (sizeof(OutT) == 2) out[row * C + c] = __float2bfloat16_rn(y);
-            else out[row * C + c] = y;
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c)), be = __ldg(reinterpret_cast<const float4 *>(beta + c));
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * g.x + be.x;
+            y.y = (v[i].y - mean) * rstd * g.y + be.y;
+            y.z = (v[i].z - mean) * rstd * g.z + be.z;
+            y.w = (v[i].w - mean) * rstd * g.w + be.w;
+            if constexpr (sizeof(OutT) == 2) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+                uint2 u;
+                u.x = *reinterpret_cast<const uint32_t *>(&lo);
+                u.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(out + row * C + c) = u;
+            } else {
+                *reinterpret_cast<float4 *>(out + row * C + c) = y;
+            }
         }
     }
 }
@@ -87,111 +104,125 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float *__restrict_
 
 // ------------------------------------------------------------------------------------------------
 // Window attention, window 4x4 (16 tokens), head_dim 16 (every STF stage: 48/3 = 96/6 = 192/12 = 384/24).
-// One warp = one window x two heads: lane = head_sub * 16 + token.  K and V rows go through shared memory;
-// every lane owns one query row and produces one 16-wide output row.  The cyclic shift, the window
+// One warp = one (window, head): S = Q K^T and O = P V are each two mma.sync.m16n8k16 (bf16 in, fp32 accumulate),
+// with the operand fragments loaded straight from the channels-last qkv rows (the S accumulator fragment IS the
+// A fragment of the second product; V is transposed in registers with movmatrix).  The scalar version spent
+// ~1100 instructions per warp on 512 shared-memory loads + 512 FMAs and was issue-bound at a quarter of the
+// HBM roofline; this one is ~100 instructions and streams qkv once.  The cyclic shift, the window
 // partition/reverse and the SW-MSA region mask are index arithmetic (stf.py:42-53,166-191,316-334).
 constexpr int WIN = 4, NTOK = 16, HD = 16;
+constexpr int ATT_WARPS = 8, ATT_JOBS_PER_WARP = 4; // per CTA: 32 (window, head) jobs share one copy of the bias table
 
-__device__ __forceinline__ void unpack8(const uint4 &u, float *f)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a)
+{
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h2);
 }
 
-__global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out,
+__global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out,
                                                                const float *__restrict__ bias_table, int B, int H, int W, int C,
                                                                int heads, int shift)
 {
     extern __shared__ float s_bias[]; // [49][heads]
-    __shared__ float s_k[4][2][NTOK][HD + 1], s_v[4][2][NTOK][HD + 1];
     for (int i = threadIdx.x; i < 49 * heads; i += blockDim.x) s_bias[i] = bias_table[i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pairs = (heads + 1) / 2;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int nWw = W / WIN, nWh = H / WIN;
-    const long long jobs = (long long)B * nWh * nWw * pairs;
-    const long long job = (long long)blockIdx.x * 4 + warp;
-    if (job >= jobs) return;
-    const int pair = (int)(job % pairs);
-    long long t = job / pairs;
+    const long long jobs = (long long)B * nWh * nWw * heads;
+    const int g = lane >> 2, tq = lane & 3;
+    for (int it = 0; it < ATT_JOBS_PER_WARP; ++it) {
+    const long long job = ((long long)blockIdx.x * ATT_WARPS + warp) * ATT_JOBS_PER_WARP + it;
+    if (job >= jobs) break; // warp-uniform
+    const int head = (int)(job % heads);
+    long long t = job / heads;
     const int ww = (int)(t % nWw); t /= nWw;
     const int wh = (int)(t % nWh);
     const int b = (int)(t / nWh);
-    const int hs_sub = lane >> 4, tok = lane & 15;
-    const int head = pair * 2 + hs_sub;
-    const bool active = head < heads;
-    const int ih = tok >> 2, iw = tok & 3;
-    // position in the shifted grid and in the original grid
-    const int hs = wh * WIN + ih, ws = ww * WIN + iw;
-    int h = hs + shift, w = ws + shift;
-    if (h >= H) h -= H;
-    if (w >= W) w -= W;
-    const long long token = ((long long)b * H + h) * W + w;
-    int label = 0;
-    if (shift > 0) {
-        const int r = hs < H - WIN ? 0 : (hs < H - shift ? 1 : 2);
-        const int c = ws < W - WIN ? 0 : (ws < W - shift ? 1 : 2);
-        label = 3 * r + c;
-    }
-    float q[HD];
-    if (active) {
-        const __nv_bfloat16 *row = qkv + token * 3 * C + head * HD;
-        float tmp[HD];
-        unpack8(*reinterpret_cast<const uint4 *>(row), q);
-        unpack8(*reinterpret_cast<const uint4 *>(row + 8), q + 8);
+
+    // the two window tokens whose rows this lane touches (g and g + 8), in the shifted and the original grid
+    long long tokA, tokB;
+    int labA = 0, labB = 0;
+    auto locate = [&](int tok, long long &token, int &label) {
+        const int hs = wh * WIN + (tok >> 2), ws = ww * WIN + (tok & 3);
+        int h = hs + shift, w = ws + shift;
+        if (h >= H) h -= H;
+        if (w >= W) w -= W;
+        token = ((long long)b * H + h) * W + w;
+        if (shift > 0) label = 3 * (hs < H - WIN ? 0 : (hs < H - shift ? 1 : 2)) + (ws < W - WIN ? 0 : (ws < W - shift ? 1 : 2));
+    };
+    locate(g, tokA, labA);
+    locate(g + 8, tokB, labB);
+    const uint32_t *rowA = reinterpret_cast<const uint32_t *>(qkv + tokA * 3 * C + head * HD) + tq;
+    const uint32_t *rowB = reinterpret_cast<const uint32_t *>(qkv + tokB * 3 * C + head * HD) + tq;
+    const int cw = C / 2; // 32-bit words between q, k and v of a token
+    uint32_t qa[4], kA0, kA1, kB0, kB1, vA0, vA1, vB0, vB1;
+    qa[0] = __ldg(rowA); qa[1] = __ldg(rowB); qa[2] = __ldg(rowA + 4); qa[3] = __ldg(rowB + 4);
+    kA0 = __ldg(rowA + cw); kA1 = __ldg(rowA + cw + 4); kB0 = __ldg(rowB + cw); kB1 = __ldg(rowB + cw + 4);
+    vA0 = __ldg(rowA + 2 * cw); vA1 = __ldg(rowA + 2 * cw + 4); vB0 = __ldg(rowB + 2 * cw); vB1 = __ldg(rowB + 2 * cw + 4);
+
+    // S[i][j] for i in {g, g+8}, j in {2tq, 2tq+1, 8+2tq, 9+2tq}
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(s0, qa, kA0, kA1); // keys 0..7
+    mma_bf16_16816(s1, qa, kB0, kB1); // keys 8..15
+    float sc[2][4]; // [row g / g+8][j slot]
+    sc[0][0] = s0[0]; sc[0][1] = s0[1]; sc[0][2] = s1[0]; sc[0][3] = s1[1];
+    sc[1][0] = s0[2]; sc[1][1] = s0[3]; sc[1][2] = s1[2]; sc[1][3] = s1[3];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) q[d] *= 0.25f; // head_dim ** -0.5
-        unpack8(*reinterpret_cast<const uint4 *>(row + C), tmp);
-        unpack8(*reinterpret_cast<const uint4 *>(row + C + 8), tmp + 8);
+    for (int r = 0; r < 2; ++r) {
+        const int i = g + 8 * r, ih = i >> 2, iw = i & 3;
+        const int li = r ? labB : labA;
+        float mx = -1e30f;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) s_k[warp][hs_sub][tok][d] = tmp[d];
-        unpack8(*reinterpret_cast<const uint4 *>(row + 2 * C), tmp);
-        unpack8(*reinterpret_cast<const uint4 *>(row + 2 * C + 8), tmp + 8);
-#pragma unroll
-        for (int d = 0; d < HD; ++d) s_v[warp][hs_sub][tok][d] = tmp[d];
-    }
-    __syncwarp();
-    if (!active) return;
-    float sc[NTOK];
-    float mx = -1e30f;
-#pragma unroll
-    for (int j = 0; j < NTOK; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) a += q[d] * s_k[warp][hs_sub][j][d];
-        const int jh = j >> 2, jw = j & 3;
-        a += s_bias[((ih - jh + WIN - 1) * (2 * WIN - 1) + (iw - jw + WIN - 1)) * heads + head];
-        if (shift > 0) {
-            const int hj = wh * WIN + jh, wj = ww * WIN + jw;
-            const int lj = 3 * (hj < H - WIN ? 0 : (hj < H - shift ? 1 : 2)) + (wj < W - WIN ? 0 : (wj < W - shift ? 1 : 2));
-            if (lj != label) a += -100.0f;
+        for (int c = 0; c < 4; ++c) {
+            const int j = (c >> 1) * 8 + 2 * tq + (c & 1), jh = j >> 2, jw = j & 3;
+            float a = sc[r][c] * 0.25f; // head_dim ** -0.5 (a power of two: same as scaling q first)
+            a += s_bias[((ih - jh + WIN - 1) * (2 * WIN - 1) + (iw - jw + WIN - 1)) * heads + head];
+            if (shift > 0) {
+                const int hj = wh * WIN + jh, wj = ww * WIN + jw;
+                const int lj = 3 * (hj < H - WIN ? 0 : (hj < H - shift ? 1 : 2)) + (wj < W - WIN ? 0 : (wj < W - shift ? 1 : 2));
+                if (lj != li) a += -100.0f;
+            }
+            sc[r][c] = a;
+            mx = fmaxf(mx, a);
         }
-        sc[j] = a;
-        mx = fmaxf(mx, a);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { sc[r][c] = __expf(sc[r][c] - mx); den += sc[r][c]; }
+        den += __shfl_xor_sync(0xffffffffu, den, 1);
+        den += __shfl_xor_sync(0xffffffffu, den, 2);
+        const float inv = 1.0f / den;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sc[r][c] *= inv;
     }
-    float den = 0.f;
-#pragma unroll
-    for (int j = 0; j < NTOK; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
-    const float inv = 1.0f / den;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < NTOK; ++j) {
-        const float pj = sc[j] * inv;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] += pj * s_v[warp][hs_sub][j][d];
+    // P as the A fragment of O = P V:  a0 = P[g][2tq..], a1 = P[g+8][2tq..], a2 = P[g][8+2tq..], a3 = P[g+8][8+2tq..]
+    uint32_t pa[4];
+    pa[0] = pack_bf16(sc[0][0], sc[0][1]); pa[1] = pack_bf16(sc[1][0], sc[1][1]);
+    pa[2] = pack_bf16(sc[0][2], sc[0][3]); pa[3] = pack_bf16(sc[1][2], sc[1][3]);
+    // B fragment for output columns d = dt*8 + g: (V[2tq][d], V[2tq+1][d]) and (V[8+2tq][d], V[9+2tq][d]) = transposed 8x8 blocks
+    const uint32_t b00 = movmatrix_trans(vA0), b01 = movmatrix_trans(vB0); // d tile 0: keys 0..7, keys 8..15
+    const uint32_t b10 = movmatrix_trans(vA1), b11 = movmatrix_trans(vB1); // d tile 1
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(o0, pa, b00, b01);
+    mma_bf16_16816(o1, pa, b10, b11);
+    uint32_t *dstA = reinterpret_cast<uint32_t *>(out + tokA * C + head * HD) + tq;
+    uint32_t *dstB = reinterpret_cast<uint32_t *>(out + tokB * C + head * HD) + tq;
+    dstA[0] = pack_bf16(o0[0], o0[1]); dstA[4] = pack_bf16(o1[0], o1[1]);
+    dstB[0] = pack_bf16(o0[2], o0[3]); dstB[4] = pack_bf16(o1[2], o1[3]);
     }
-    uint32_t pk[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * d], o[2 * d + 1]);
-        pk[d] = *reinterpret_cast<const uint32_t *>(&h2);
-    }
-    uint4 *dst = reinterpret_cast<uint4 *>(out + token * C + head * HD);
-    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,20 +339,21 @@ extern "C" int icm_layernorm(const float *d_in, const float *d_gamma, const floa
     ICM_CHECK_ARG(C > 0 && C <= 768, "icm_layernorm: C=%d outside (0,768]", C);
     ICM_CHECK_ARG(!gather || (C % 4 == 0 && rows == (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2)), "icm_layernorm: gather shape mismatch");
     ICM_CHECK_ARG(rows > 0, "icm_layernorm: no rows");
-    const unsigned grid = (unsigned)((rows + 7) / 8);
+    ICM_CHECK_ARG(C % 4 == 0 && (!gather || C % 16 == 0), "icm_layernorm: C=%d must be a multiple of 4 (16 with gather)", C);
     cudaStream_t st = as_stream(stream);
-#define ICM_LN_LAUNCH(V)                                                                                                   \
+#define ICM_LN_LAUNCH(LPR, NQ)                                                                                             \
     do {                                                                                                                   \
+        const unsigned grid = (unsigned)((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR)));                                  \
         if (out_dtype == ICM_OUT_BF16)                                                                                     \
-            layernorm_kernel<__nv_bfloat16, V><<<grid, 256, 0, st>>>(d_in, d_gamma, d_beta, (__nv_bfloat16 *)d_out, rows, C, gather, H, W); \
+            layernorm_kernel<__nv_bfloat16, LPR, NQ><<<grid, 256, 0, st>>>(d_in, d_gamma, d_beta, (__nv_bfloat16 *)d_out, rows, C, gather, H, W); \
         else                                                                                                               \
-            layernorm_kernel<float, V><<<grid, 256, 0, st>>>(d_in, d_gamma, d_beta, (float *)d_out, rows, C, gather, H, W);  \
+            layernorm_kernel<float, LPR, NQ><<<grid, 256, 0, st>>>(d_in, d_gamma, d_beta, (float *)d_out, rows, C, gather, H, W);  \
     } while (0)
-    if (C <= 64) ICM_LN_LAUNCH(2);
-    else if (C <= 128) ICM_LN_LAUNCH(4);
-    else if (C <= 256) ICM_LN_LAUNCH(8);
-    else if (C <= 384) ICM_LN_LAUNCH(12);
-    else ICM_LN_LAUNCH(24);
+    if (C <= 48) ICM_LN_LAUNCH(4, 3);
+    else if (C <= 96) ICM_LN_LAUNCH(8, 3);
+    else if (C <= 192) ICM_LN_LAUNCH(16, 3);
+    else if (C <= 384) ICM_LN_LAUNCH(32, 3);
+    else ICM_LN_LAUNCH(32, 6);
 #undef ICM_LN_LAUNCH
     ICM_LAUNCH_CHECK();
     return ICM_OK;
@@ -344,9 +376,10 @@ extern "C" int icm_window_attention(const void *d_qkv, void *d_out, const float 
     if (window != WIN || C != heads * HD) { set_error("icm_window_attention: only window 4 / head_dim 16 is built (got window %d, head_dim %d)", window, heads ? C / heads : 0); return ICM_ERR_UNSUPPORTED; }
     if (H % WIN || W % WIN) { set_error("icm_window_attention: H=%d W=%d must be multiples of the window (pad the image to a multiple of 64 as the reference's eval does)", H, W); return ICM_ERR_UNSUPPORTED; }
     ICM_CHECK_ARG(shift >= 0 && shift < WIN, "icm_window_attention: bad shift");
-    const long long jobs = (long long)B * (H / WIN) * (W / WIN) * ((heads + 1) / 2);
-    const unsigned grid = (unsigned)((jobs + 3) / 4);
-    window_attention_kernel<<<grid, 128, 49 * heads * sizeof(float), as_stream(stream)>>>(
+    const long long jobs = (long long)B * (H / WIN) * (W / WIN) * heads;
+    const int per_cta = ATT_WARPS * ATT_JOBS_PER_WARP;
+    const unsigned grid = (unsigned)((jobs + per_cta - 1) / per_cta);
+    window_attention_kernel<<<grid, ATT_WARPS * 32, 49 * heads * sizeof(float), as_stream(stream)>>>(
         (const __nv_bfloat16 *)d_qkv, (__nv_bfloat16 *)d_out, d_bias_table, B, H, W, C, heads, shift);
     ICM_LAUNCH_CHECK();
     return ICM_OK;

@@ -83,7 +83,7 @@ int icm_rans_decoder_set_streams(icm_rans_decoder *d, const uint8_t *d_bytes, co
 /* Same, for streams that are already on the device as icm_rans_encode_batch left them: d_bytes = its
  * d_packed, d_sizes = its int32 byte sizes (streams back to back in order).  No host synchronisation. */
 int icm_rans_decoder_set_streams_device(icm_rans_decoder *d, const uint8_t *d_bytes, const int32_t *d_sizes, void *stream);
-/* Streams per decoder CTA: 1, 2 or 4 (0 = automatic: 1 up to 74 streams).  See csrc/rans.cu. */
+/* Streams per decoder CTA: 1, 2, 4, 8 or 16 (0 = automatic: 1 up to 74 streams).  See csrc/rans.cu. */
 int icm_set_decoder_streams_per_cta(int n);
 /* Decodes the next n_per_stream symbols of every stream.  d_indexes / d_out: [n_streams][n_per_stream]. */
 int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, const int32_t *d_indexes,
