@@ -233,13 +233,15 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float *__restric
                                                           int B, int H, int W, int C)
 {
     __shared__ float s_w[64 * 12], s_b[64], s_g[64], s_be[64];
+    extern __shared__ float s_o[]; // [blockDim.x][C + 1]
     for (int i = threadIdx.x; i < C * 12; i += blockDim.x) s_w[i] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_b[i] = bias[i]; s_g[i] = gamma[i]; s_be[i] = beta[i]; }
     __syncthreads();
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
     const long long total = (long long)B * H2 * W2;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx0 < total;
+    const long long idx = live ? idx0 : total - 1;
     const int w2 = (int)(idx % W2);
     const int h2 = (int)((idx / W2) % H2);
     const int b = (int)(idx / ((long long)W2 * H2));
@@ -271,9 +273,18 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float *__restric
 #pragma unroll
     for (int c = 0; c < 64; ++c) if (c < C) { const float d = y[c] - mean; sq += d * d; }
     const float rstd = rsqrtf(sq / (float)C + 1e-5f);
-    float *dst = tokens + idx * C;
+    // each thread owns one token (C contiguous floats): go through shared memory so that the CTA's 128 x C block,
+    // which is contiguous in the token tensor, is written with coalesced stores
+    float *mine = s_o + threadIdx.x * (C + 1);
+    if (live) {
 #pragma unroll
-    for (int c = 0; c < 64; ++c) if (c < C) dst[c] = (y[c] - mean) * rstd * s_g[c] + s_be[c];
+        for (int c = 0; c < 64; ++c) if (c < C) mine[c] = (y[c] - mean) * rstd * s_g[c] + s_be[c];
+    }
+    __syncthreads();
+    const long long first = (long long)blockIdx.x * blockDim.x;
+    const int n_tok = (int)min((long long)blockDim.x, total - first);
+    float *dst = tokens + first * C;
+    for (int i = threadIdx.x; i < n_tok * C; i += blockDim.x) dst[i] = s_o[(i / C) * (C + 1) + (i % C)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -325,6 +336,103 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const __nv_bfloat16 *__
         const long long plane = (long long)H * W;
         float *dst = img + (long long)b * 3 * plane + (long long)oh * W + ow;
         dst[0] = acc0; dst[plane] = acc1; dst[2 * plane] = acc2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output convolution 48 -> 3 on the tensor cores: per warp 32 pixels of one image row as two m16n8k16 tiles
+// (M = 16 pixels, N = 8 output channels of which 3 are real, K = 16 input channels), 9 taps x 3 k-steps each.
+// The CTA (8 warps = 8 rows x 32 pixels) stages its 10 x 34 halo tile in shared memory with a 112-byte pixel
+// pitch (conflict-free ldmatrix rows); the 27 weight fragments live in registers; results leave through a small
+// shared-memory transpose as 128-byte rows of the three NCHW planes.  The CUDA-core version above (kept for
+// other channel counts) was FMA/LDS-bound at 5.5 ms per 64 images; N = 16 on tcgen05 would be bound by the
+// 9-fold re-read of the A tile from L2 instead.
+constexpr int FC_C = 48, FC_TW = 32, FC_TH = 8, FC_VT = 4, FC_PITCH = 112; // bytes per halo pixel (96 + 16 pad)
+
+__global__ void __launch_bounds__(256) final_conv48_mma_kernel(const __nv_bfloat16 *__restrict__ in, const float *__restrict__ w,
+                                                               const float *__restrict__ bias, float *__restrict__ img, int B, int H,
+                                                               int W, int clamp01)
+{
+    __shared__ __align__(16) unsigned char s_tile[(FC_TH + 2) * (FC_TW + 2) * FC_PITCH];
+    __shared__ float s_out[FC_TH][3][FC_TW];
+    __shared__ uint2 s_wf[27][32];
+    const int b = blockIdx.z, w0 = blockIdx.x * FC_TW;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    // weight fragments, built once per CTA in lane order: B[k = channel][n = co] = w[co][channel][tap]; lane (g, t) holds
+    // k = 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1) of n = g
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
+        const int l = i & 31, frag = i >> 5, tap = frag / 3, ks = frag - tap * 3;
+        const int fg = l >> 2, ft = l & 3;
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        if (fg < 3) {
+            const int c0 = ks * 16 + 2 * ft;
+            f[0] = w[(fg * FC_C + c0) * 9 + tap];     f[1] = w[(fg * FC_C + c0 + 1) * 9 + tap];
+            f[2] = w[(fg * FC_C + c0 + 8) * 9 + tap]; f[3] = w[(fg * FC_C + c0 + 9) * 9 + tap];
+        }
+        s_wf[frag][l] = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+    }
+    const int g = lane >> 2, t = lane & 3;
+    for (int vt = 0; vt < FC_VT; ++vt) {
+    const int h0 = (blockIdx.y * FC_VT + vt) * FC_TH;
+    if (h0 >= H) break;
+    if (vt) __syncthreads(); // the previous tile has been consumed
+    // halo tile: 6 x 16-byte pieces per pixel
+    for (int i = threadIdx.x; i < (FC_TH + 2) * (FC_TW + 2) * 6; i += blockDim.x) {
+        const int piece = i % 6, pix = i / 6;
+        const int hh = h0 + pix / (FC_TW + 2) - 1, ww = w0 + pix % (FC_TW + 2) - 1;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            v = __ldg(reinterpret_cast<const uint4 *>(in + (((long long)b * H + hh) * W + ww) * FC_C) + piece);
+        *reinterpret_cast<uint4 *>(s_tile + pix * FC_PITCH + piece * 16) = v;
+    }
+    __syncthreads();
+    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(s_tile);
+    // ldmatrix.x4 row address of this lane: pixel row (lane % 16), channel half (lane / 16)
+    const int lrow = lane & 15, lhalf = lane >> 4;
+    float acc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t row_addr = tile_addr + (uint32_t)(((warp + dy) * (FC_TW + 2) + mt * 16 + lrow + dx) * FC_PITCH + lhalf * 16);
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                uint32_t a[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(row_addr + ks * 32));
+                const uint2 wb = s_wf[tap * 3 + ks][lane];
+                mma_bf16_16816(acc[mt], a, wb.x, wb.y);
+            }
+        }
+    }
+    // acc[mt][0..1]: pixel mt*16 + g, co 2t, 2t+1;  acc[mt][2..3]: pixel mt*16 + g + 8
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        if (t == 0) {
+            s_out[warp][0][mt * 16 + g] = acc[mt][0]; s_out[warp][1][mt * 16 + g] = acc[mt][1];
+            s_out[warp][0][mt * 16 + g + 8] = acc[mt][2]; s_out[warp][1][mt * 16 + g + 8] = acc[mt][3];
+        } else if (t == 1) {
+            s_out[warp][2][mt * 16 + g] = acc[mt][0];
+            s_out[warp][2][mt * 16 + g + 8] = acc[mt][2];
+        }
+    }
+    __syncwarp();
+    const int oh = h0 + warp, ow = w0 + lane;
+    if (oh < H && ow < W) {
+        const long long plane = (long long)H * W;
+        float *dst = img + (long long)b * 3 * plane + (long long)oh * W + ow;
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            float v = s_out[warp][co][lane] + bias[co];
+            if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+            dst[co * plane] = v;
+        }
+    }
     }
 }
 
@@ -391,7 +499,7 @@ extern "C" int icm_patch_embed(const float *d_img, const float *d_w, const float
     ICM_CHECK_ARG(d_img && d_w && d_b && d_gamma && d_beta && d_tokens, "icm_patch_embed: null argument");
     ICM_CHECK_ARG(C > 0 && C <= 64 && B > 0 && H > 0 && W > 0, "icm_patch_embed: bad shape");
     const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
-    patch_embed_kernel<<<(unsigned)((total + 127) / 128), 128, 0, as_stream(stream)>>>(d_img, d_w, d_b, d_gamma, d_beta, d_tokens, B, H, W, C);
+    patch_embed_kernel<<<(unsigned)((total + 127) / 128), 128, (size_t)128 * (C + 1) * sizeof(float), as_stream(stream)>>>(d_img, d_w, d_b, d_gamma, d_beta, d_tokens, B, H, W, C);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }
@@ -401,6 +509,12 @@ extern "C" int icm_final_conv(const void *d_in_bf16, const float *d_w, const flo
 {
     ICM_CHECK_ARG(d_in_bf16 && d_w && d_b && d_img, "icm_final_conv: null argument");
     ICM_CHECK_ARG(C > 0 && C % 2 == 0 && C <= 96, "icm_final_conv: C=%d unsupported", C);
+    if (C == FC_C && (((uintptr_t)d_in_bf16) & 15) == 0) { // the reference's end_conv[2]: tensor-core kernel
+        dim3 g((W + FC_TW - 1) / FC_TW, (H + FC_TH * FC_VT - 1) / (FC_TH * FC_VT), B);
+        final_conv48_mma_kernel<<<g, 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)d_in_bf16, d_w, d_b, d_img, B, H, W, clamp01);
+        ICM_LAUNCH_CHECK();
+        return ICM_OK;
+    }
     const size_t smem = (size_t)(FT + 2) * (FT + 2) * (C / 2 + 1) * 4 + (size_t)27 * C * 4;
     dim3 grid((W + FT - 1) / FT, (H + FT - 1) / FT, B);
     static thread_local bool configured = false;

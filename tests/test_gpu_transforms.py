@@ -149,7 +149,7 @@ def test_patch_embed_and_final_conv(eng):
     from compressai._native import check, lib, stream_ptr
 
     g = torch.Generator().manual_seed(4)
-    B, H, W = 2, 20, 28
+    B, H, W = 2, 44, 70  # not multiples of the 32x32 CTA tile of the output convolution
     img = torch.rand(B, 3, H, W, generator=g)
     w, b = torch.randn(48, 3, 2, 2, generator=g) * 0.3, torch.randn(48, generator=g) * 0.1
     gam, bet = 1 + 0.1 * torch.randn(48, generator=g), 0.1 * torch.randn(48, generator=g)
@@ -162,7 +162,7 @@ def test_patch_embed_and_final_conv(eng):
     _close(out, ref, rtol=1e-4, atol=1e-4)
     x = torch.randn(B, 48, H, W, generator=g)
     w3, b3 = torch.randn(3, 48, 3, 3, generator=g) * 0.1, torch.randn(3, generator=g) * 0.1
-    ref = F.conv2d(_bf(x), w3, b3, padding=1)
+    ref = F.conv2d(_bf(x), _bf(w3), b3, padding=1)  # bf16 operands (tensor-core kernel), fp32 accumulation
     xin = c(x.permute(0, 2, 3, 1).reshape(-1, 48)).bfloat16()
     for clamp in (0, 1):
         o = torch.empty(B, 3, H, W, device="cuda")
