@@ -117,33 +117,31 @@ struct ConvParams {
     int KH, KW, stride, pad;
     int BN, Cout, stages, tmem_cols; // tmem_cols = two accumulators
     int n_tiles, total_tiles;
+    unsigned long long fd_n, fd_w, fd_h; // ceil(2^40 / d) for d = n_tiles, tiles_w, tiles_h (0 when d == 1)
     int act, out_dtype, pixel_shuffle;
     long long out_pitch, res_pitch;
+    int wide_st, wide_ld;    // output / second-operand rows and base are 32-byte aligned: 256-bit stores / loads
     int res_dtype, res_mode; // residual operand: fp32 / bf16; added after act (0), before act (1), multiplied (2)
     const float *bias;
     const void *residual;
     void *out;
 };
 
-// exact-form GELU 0.5 v (1 + erf(v / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
-// below the bf16 rounding of the stored activation): 2 MUFU + ~10 FMA instead of libdevice erff's ~30
-// instructions -- the epilogue of the GELU linears is otherwise ALU-bound.
+// erf-GELU v * Phi(v) as v * sigmoid(P(v)), P an odd minimax polynomial of min(max(v, -5), 5): |error| <= 2.6e-5
+// absolute over all v (fitted against 0.5 v (1 + erf(v / sqrt 2)); the tanh form is 10x worse), a sixteenth of the
+// bf16 rounding of a stored activation of magnitude 0.1.  10 instructions (2 MUFU) per element; the
+// Abramowitz-Stegun 7.1.26 form used before took 16.5 and libdevice erff ~30, and the epilogue of the GELU linears
+// is instruction-issue-bound (~20 instructions per output against a budget of 14 at the HBM roofline).
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __device__ __forceinline__ float gelu_erf(float v)
 {
-    const float u = fabsf(v) * 0.70710678118654752440f;
-    const float t = mufu_rcp(fmaf(0.3275911f, u, 1.0f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    poly *= t;
-    const float e = mufu_ex2(-1.4426950408889634f * u * u);
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    const float h = 0.5f * v;
-    return fmaf(fabsf(h), erf_abs, h); // v * erf(v / sqrt 2) is even in v
+    const float c = fminf(fmaxf(v, -5.0f), 5.0f);
+    const float c2 = c * c;
+    float p = fmaf(0.0010142815299332142f, c2, -0.10677584260702133f); // coefficients pre-multiplied by -log2(e)
+    p = fmaf(p, c2, -2.301121234893799f);
+    return v * mufu_rcp(1.0f + mufu_ex2(p * c));
 }
 
 // The activation switch sits OUTSIDE the 16-element loop (one uniform branch per chunk): with it inside, the
@@ -192,7 +190,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // layout: [stages][A 16 KB][B BN*128 B] | barriers | tmem slot
+    // layout: [stages][A 16 KB][B BN*128 B] | barriers | tmem slot | bias
     const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.BN * BK * 2;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
     unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
@@ -201,6 +199,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t *acc_full = empty_bar + MAX_STAGES; // [2] MMA -> epilogue
     uint64_t *acc_empty = acc_full + 2;          // [2] epilogue -> MMA
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *s_bias = reinterpret_cast<float *>(tmem_slot + 4); // [n_tiles * BN], zeros without a bias
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TW = 1 << p.TW_log2, TH = BM >> p.TW_log2;
@@ -212,6 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += blockDim.x) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
     if (warp == 1) { // TMEM allocation is warp-collective
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -222,11 +222,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     // tile id -> (n tile fastest, then w, h, image)
+    // (three runtime integer divisions cost ~100 instructions per tile: 10 % of the epilogue of a K = 48 linear)
+    auto fdiv = [](uint32_t n, unsigned long long m) -> uint32_t { return m ? (uint32_t)(((unsigned long long)n * m) >> 40) : n; };
     auto tile_coords = [&](int tile, int &n0, int &w0, int &h0, int &b) {
-        const int nt = tile % p.n_tiles; tile /= p.n_tiles;
-        const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
-        const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
-        n0 = nt * p.BN; w0 = tw_i * TW; h0 = th_i * TH; b = tile;
+        uint32_t t = (uint32_t)tile, q = fdiv(t, p.fd_n);
+        const int nt = (int)(t - q * (uint32_t)p.n_tiles); t = q;
+        q = fdiv(t, p.fd_w);
+        const int tw_i = (int)(t - q * (uint32_t)p.tiles_w); t = q;
+        q = fdiv(t, p.fd_h);
+        const int th_i = (int)(t - q * (uint32_t)p.tiles_h);
+        n0 = nt * p.BN; w0 = tw_i * TW; h0 = th_i * TH; b = (int)q;
     };
 
     if (warp == 0) {
@@ -290,8 +295,102 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int r = q * 32 + lane;
         const int th = r >> p.TW_log2, tw = r & (TW - 1);
         const int Cq = p.pixel_shuffle ? p.Cout / (p.pixel_shuffle * p.pixel_shuffle) : 0;
+        const int n_chunks = p.BN / 16;
         int acc = 0;
         uint32_t acc_phase = 0;
+        // one 16-column chunk: bias, second operand, activation, store
+        auto finish = [&](uint32_t (&accv)[16], int n, bool valid, long long pix, int b, int oh, int ow) {
+            if (!valid || n >= p.Cout) return;
+            float v[16];
+            {
+                const float4 *bp = reinterpret_cast<const float4 *>(s_bias + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = bp[j];
+                    v[4 * j] = __uint_as_float(accv[4 * j]) + t.x; v[4 * j + 1] = __uint_as_float(accv[4 * j + 1]) + t.y;
+                    v[4 * j + 2] = __uint_as_float(accv[4 * j + 2]) + t.z; v[4 * j + 3] = __uint_as_float(accv[4 * j + 3]) + t.w;
+                }
+            }
+            // second operand of the epilogue: fp32 (residual stream) or bf16 (activations); loaded where it is applied so
+            // that no 16-register copy of it is live across the activation
+            auto combine = [&](int mode) {
+                float rv[16];
+                if (p.res_dtype == ICM_OUT_F32) {
+                    const float *rp = reinterpret_cast<const float *>(p.residual) + pix * p.res_pitch + n;
+                    if (p.wide_ld) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(rv[8 * j]), "=f"(rv[8 * j + 1]), "=f"(rv[8 * j + 2]),
+                                         "=f"(rv[8 * j + 3]), "=f"(rv[8 * j + 4]), "=f"(rv[8 * j + 5]), "=f"(rv[8 * j + 6]), "=f"(rv[8 * j + 7]) : "l"(rp + 8 * j));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const float4 t = __ldg(reinterpret_cast<const float4 *>(rp) + j); rv[4 * j] = t.x; rv[4 * j + 1] = t.y; rv[4 * j + 2] = t.z; rv[4 * j + 3] = t.w; }
+                    }
+                } else {
+                    const __nv_bfloat16 *rp = reinterpret_cast<const __nv_bfloat16 *>(p.residual) + pix * p.res_pitch + n;
+                    uint32_t u[8];
+                    if (p.wide_ld) {
+                        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]),
+                                     "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "l"(rp));
+                    } else {
+                        const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(rp)), t1 = __ldg(reinterpret_cast<const uint4 *>(rp) + 1);
+                        u[0] = t0.x; u[1] = t0.y; u[2] = t0.z; u[3] = t0.w; u[4] = t1.x; u[5] = t1.y; u[6] = t1.z; u[7] = t1.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u[k]));
+                        rv[2 * k] = f.x; rv[2 * k + 1] = f.y;
+                    }
+                }
+                if (mode == 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= rv[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                }
+            };
+            if (p.residual && p.res_mode == 1) combine(1);
+            apply_act16(v, p.act);
+            long long off;
+            if (p.pixel_shuffle) {
+                const int rr = p.pixel_shuffle;
+                const int quad = n / Cq, c = n - quad * Cq;
+                const int i = quad / rr, jj = quad - i * rr;
+                off = (((long long)b * p.Ho * rr + (long long)oh * rr + i) * ((long long)p.Wo * rr) + (long long)ow * rr + jj) * p.out_pitch + c;
+            } else {
+                off = pix * p.out_pitch + n;
+            }
+            if (p.residual && p.res_mode != 1) combine(p.res_mode);
+            // 32-byte stores (st.global.v8, sm_100): one full sector per lane and instruction instead of two half-sector writes
+            if (p.out_dtype == ICM_OUT_F32) {
+                float *op = reinterpret_cast<float *>(p.out) + off;
+                if (p.wide_st) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op + 8 * j), "f"(v[8 * j]), "f"(v[8 * j + 1]),
+                                     "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]), "f"(v[8 * j + 6]), "f"(v[8 * j + 7]) : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) reinterpret_cast<float4 *>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            } else {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
+                }
+                __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(p.out) + off;
+                if (p.wide_st) {
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                                 "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                } else {
+                    reinterpret_cast<uint4 *>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4 *>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+        };
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int n0, w0, h0, b;
             tile_coords(tile, n0, w0, h0, b);
@@ -301,80 +400,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_wait(&acc_full[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-            for (int c16 = grp; c16 < p.BN / 16; c16 += EPI_WARPS / 4) {
-                uint32_t accv[16];
-                tmem_ld16(tmem_d + (uint32_t)(c16 * 16), accv);
+            // Software pipeline over this warp's chunks: the TMEM load of chunk i+1 is in flight while chunk i is
+            // finished (ncu: 35 % of the epilogue's stall samples sat on the exposed tcgen05.ld / bias latency), and the
+            // accumulator goes back to the MMA warp as soon as the last load has landed, before its chunk is finished.
+            uint32_t ra[16], rb[16];
+            int c16 = grp;
+            bool released = false;
+            auto release = [&]() {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                released = true;
+            };
+            if (c16 < n_chunks) tmem_ld16(tmem_d + (uint32_t)(c16 * 16), ra);
+            while (c16 < n_chunks) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int n = n0 + c16 * 16;
-                if (!valid || n >= p.Cout) continue;
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(accv[j]);
-                if (p.bias) {
-                    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + n);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { const float4 t = __ldg(bp + j); v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
-                }
-                float rv[16];
-                if (p.residual) { // second operand of the epilogue: fp32 (residual stream) or bf16 (activations)
-                    if (p.res_dtype == ICM_OUT_F32) {
-                        const float4 *rp = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.residual) + pix * p.res_pitch + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { const float4 t = __ldg(rp + j); rv[4 * j] = t.x; rv[4 * j + 1] = t.y; rv[4 * j + 2] = t.z; rv[4 * j + 3] = t.w; }
-                    } else {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(p.residual) + pix * p.res_pitch + n);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint4 t = __ldg(rp + j);
-                            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); rv[8 * j + 2 * k] = f.x; rv[8 * j + 2 * k + 1] = f.y; }
-                        }
-                    }
-                    if (p.res_mode == 1) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += rv[j];
-                    }
-                }
-                apply_act16(v, p.act);
-                long long off;
-                if (p.pixel_shuffle) {
-                    const int rr = p.pixel_shuffle;
-                    const int quad = n / Cq, c = n - quad * Cq;
-                    const int i = quad / rr, jj = quad - i * rr;
-                    off = (((long long)b * p.Ho * rr + (long long)oh * rr + i) * ((long long)p.Wo * rr) + (long long)ow * rr + jj) * p.out_pitch + c;
-                } else {
-                    off = pix * p.out_pitch + n;
-                }
-                if (p.residual) {
-                    if (p.res_mode == 0) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += rv[j];
-                    } else if (p.res_mode == 2) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] *= rv[j];
-                    }
-                }
-                if (p.out_dtype == ICM_OUT_F32) {
-                    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + off);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                    }
-                    uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + off);
-                    op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                }
+                if (c16 + 4 < n_chunks) tmem_ld16(tmem_d + (uint32_t)((c16 + 4) * 16), rb); else release();
+                finish(ra, n0 + c16 * 16, valid, pix, b, oh, ow);
+                c16 += 4;
+                if (c16 >= n_chunks) break;
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c16 + 4 < n_chunks) tmem_ld16(tmem_d + (uint32_t)((c16 + 4) * 16), ra); else release();
+                finish(rb, n0 + c16 * 16, valid, pix, b, oh, ow);
+                c16 += 4;
             }
-            // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (!released) release(); // a warp with no chunk of this tile
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -503,6 +553,13 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.out_pitch = a->out_pitch; p.res_pitch = a->res_pitch;
     p.bias = a->bias; p.residual = a->residual; p.out = a->out;
     p.res_dtype = a->res_dtype; p.res_mode = a->res_mode;
+    {
+        const long long es = a->out_dtype == ICM_OUT_F32 ? 4 : 2;
+        const int cq = ps ? a->Cout / (ps * ps) : 16;
+        const long long rs = a->res_dtype == ICM_OUT_F32 ? 4 : 2;
+        p.wide_ld = a->residual && ((uintptr_t)a->residual % 32 == 0) && ((long long)a->res_pitch * rs % 32 == 0);
+        p.wide_st = ((uintptr_t)a->out % 32 == 0) && ((long long)a->out_pitch * es % 32 == 0) && (cq * es % 32 == 0);
+    }
     ICM_CHECK_ARG(a->res_mode >= 0 && a->res_mode <= 2 && (a->res_dtype == ICM_OUT_F32 || a->res_dtype == ICM_OUT_BF16), "icm_conv2d: bad residual mode/dtype");
     ICM_CHECK_ARG(a->out_pitch % (a->out_dtype == ICM_OUT_F32 ? 4 : 8) == 0, "icm_conv2d: out_pitch=%d breaks 16-byte store alignment", a->out_pitch);
     ICM_CHECK_ARG(!a->residual || (a->res_pitch % (a->res_dtype == ICM_OUT_F32 ? 4 : 8) == 0 && ((uintptr_t)a->residual & 15) == 0), "icm_conv2d: residual must be 16-byte aligned");
@@ -531,15 +588,19 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("icm_conv2d: cuTensorMapEncodeTiled(W) failed (%d)", (int)r); return ICM_ERR_CUDA; }
     }
-    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
+    p.n_tiles = (a->Cout + p.BN - 1) / p.BN;
+    const size_t bias_bytes = (size_t)p.n_tiles * p.BN * 4;
+    ICM_CHECK_ARG(bias_bytes <= 16 * 1024, "icm_conv2d: Cout=%d too wide for the bias staging area", a->Cout);
+    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4) * 8 + 16 + bias_bytes;
     static thread_local size_t configured = 0;
     if (smem_bytes > configured) {
         ICM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = 227 * 1024;
     }
-    p.n_tiles = (a->Cout + p.BN - 1) / p.BN;
-    ICM_CHECK_ARG(m_tiles * p.n_tiles <= 0x7FFFFFFF, "icm_conv2d: too many tiles");
+    ICM_CHECK_ARG(m_tiles * p.n_tiles < (1 << 24) && p.tiles_w < 65536 && p.tiles_h < 65536, "icm_conv2d: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);
+    auto magic = [](int d) -> unsigned long long { return d <= 1 ? 0ull : ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; };
+    p.fd_n = magic(p.n_tiles); p.fd_w = magic(p.tiles_w); p.fd_h = magic(p.tiles_h);
     int max_ctas = sm_count();
     if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
     const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
