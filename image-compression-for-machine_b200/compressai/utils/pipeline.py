@@ -32,7 +32,7 @@ class RoundTripPipeline:
     up to `lag` other jobs run beside them.  Without the chain all jobs start in lockstep, reach their coders
     together and leave the GPU idle (measured run-to-run spread 400-530 images/s)."""
 
-    def __init__(self, model, n_streams=12, part=16, conv_sm_limit=None, decoder_streams_per_cta=4, lag=6, chains=2):
+    def __init__(self, model, n_streams=10, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=6, chains=2):
         self.model = model
         self.decoder_streams_per_cta = int(decoder_streams_per_cta)
         # The decoder's CTAs (~155 KB of shared memory) cannot share an SM with a persistent conv CTA (~200 KB); the
@@ -85,10 +85,11 @@ class RoundTripPipeline:
         return hook
 
     @torch.no_grad()
-    def roundtrip(self, batches, host_io=False, out_host=None):
+    def roundtrip(self, batches, host_io=False, out_host=None, keep_outputs=True):
         """compress + decompress every batch of `batches` ([B,3,H,W] CUDA tensors, or pinned host tensors with
         host_io=True).  Returns (x_hats, strings): x_hats per batch (CUDA, or written into `out_host`), strings per
-        batch as [[y bytes...], [z bytes...]] when host_io else None."""
+        batch as [[y bytes...], [z bytes...]] when host_io else None.  keep_outputs=False drops each job's x_hat as soon as
+        it has been produced (or copied to `out_host`), so its memory is reused by the next job of that stream."""
         m = self.model
         dev = m.entropy_bottleneck.quantiles.device
         self._setup(dev)
@@ -147,7 +148,8 @@ class RoundTripPipeline:
                     hook("end")
                 if out_host is not None:
                     out_host[bi][lo:hi].copy_(x_hat, non_blocking=True)
-                results[bi].append(x_hat)
+                if keep_outputs and out_host is None:
+                    results[bi].append(x_hat)
 
         try:
             for t in range(len(jobs) + lag):
@@ -161,7 +163,7 @@ class RoundTripPipeline:
             check(lib().icm_set_conv_sm_limit(0), "icm_set_conv_sm_limit")
             check(lib().icm_set_decoder_streams_per_cta(0), "icm_set_decoder_streams_per_cta")
         x_hats = None
-        if out_host is None:
+        if out_host is None and keep_outputs:
             x_hats = []
             for parts in results:
                 for t in parts:

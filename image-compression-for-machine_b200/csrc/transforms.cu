@@ -164,13 +164,16 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
     };
     locate(g, tokA, labA);
     locate(g + 8, tokB, labB);
-    const uint32_t *rowA = reinterpret_cast<const uint32_t *>(qkv + tokA * 3 * C + head * HD) + tq;
-    const uint32_t *rowB = reinterpret_cast<const uint32_t *>(qkv + tokB * 3 * C + head * HD) + tq;
-    const int cw = C / 2; // 32-bit words between q, k and v of a token
-    uint32_t qa[4], kA0, kA1, kB0, kB1, vA0, vA1, vB0, vB1;
-    qa[0] = __ldg(rowA); qa[1] = __ldg(rowB); qa[2] = __ldg(rowA + 4); qa[3] = __ldg(rowB + 4);
-    kA0 = __ldg(rowA + cw); kA1 = __ldg(rowA + cw + 4); kB0 = __ldg(rowB + cw); kB1 = __ldg(rowB + cw + 4);
-    vA0 = __ldg(rowA + 2 * cw); vA1 = __ldg(rowA + 2 * cw + 4); vB0 = __ldg(rowB + 2 * cw); vB1 = __ldg(rowB + 2 * cw + 4);
+    // The contraction index d of S = Q K^T and the output column d of O = P V may be permuted freely as long as Q, K, V
+    // and O agree: fragment slots (2tq, 2tq+1, 8+2tq, 9+2tq) hold head channels 4tq .. 4tq+3, so every operand is ONE
+    // 8-byte load per row and lane (4 lanes = one full 32-byte sector) and the output one 8-byte store.
+    const uint2 *rowA = reinterpret_cast<const uint2 *>(qkv + tokA * 3 * C + head * HD) + tq;
+    const uint2 *rowB = reinterpret_cast<const uint2 *>(qkv + tokB * 3 * C + head * HD) + tq;
+    const int cw = C / 4; // 8-byte words between q, k and v of a token
+    const uint2 qA = __ldg(rowA), qB = __ldg(rowB), kA = __ldg(rowA + cw), kB = __ldg(rowB + cw), vA = __ldg(rowA + 2 * cw), vB = __ldg(rowB + 2 * cw);
+    uint32_t qa[4];
+    qa[0] = qA.x; qa[1] = qB.x; qa[2] = qA.y; qa[3] = qB.y;
+    const uint32_t kA0 = kA.x, kA1 = kA.y, kB0 = kB.x, kB1 = kB.y, vA0 = vA.x, vA1 = vA.y, vB0 = vB.x, vB1 = vB.y;
 
     // S[i][j] for i in {g, g+8}, j in {2tq, 2tq+1, 8+2tq, 9+2tq}
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -218,10 +221,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const 
     float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
     mma_bf16_16816(o0, pa, b00, b01);
     mma_bf16_16816(o1, pa, b10, b11);
-    uint32_t *dstA = reinterpret_cast<uint32_t *>(out + tokA * C + head * HD) + tq;
-    uint32_t *dstB = reinterpret_cast<uint32_t *>(out + tokB * C + head * HD) + tq;
-    dstA[0] = pack_bf16(o0[0], o0[1]); dstA[4] = pack_bf16(o1[0], o1[1]);
-    dstB[0] = pack_bf16(o0[2], o0[3]); dstB[4] = pack_bf16(o1[2], o1[3]);
+    // fragment columns (2tq, 2tq+1) of d tile 0 / 1 are head channels (4tq, 4tq+1) / (4tq+2, 4tq+3)
+    *(reinterpret_cast<uint2 *>(out + tokA * C + head * HD) + tq) = make_uint2(pack_bf16(o0[0], o0[1]), pack_bf16(o1[0], o1[1]));
+    *(reinterpret_cast<uint2 *>(out + tokB * C + head * HD) + tq) = make_uint2(pack_bf16(o0[2], o0[3]), pack_bf16(o1[2], o1[3]));
     }
 }
 
