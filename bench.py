@@ -183,15 +183,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core this process may run on
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
         mm = make_model("cpu", args.weights)  # parameter container only; the timed path below is oracle/ on the CPU
-        ips, dt = cpu_baseline(mm.state_dict(), 1, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        ips, dt = cpu_baseline(mm.state_dict(), 2, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         cores = torch.get_num_threads()
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "1 image (3x768x512) compress+decompress per step, oracle/stf_ref.py fp32 + oracle/rans_oracle.c"},
+                             "sample": "2 images (3x768x512) compress+decompress per step, oracle/stf_ref.py fp32 + oracle/rans_oracle.c"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
@@ -327,6 +329,7 @@ def main():
                              "streams_in_flight": B}}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
         ips, dt = cpu_baseline(model.state_dict(), 2, steps=1, warmup=0)
         cpu = {"value": round(ips, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"2 images (3x768x512) compress+decompress once ({dt:.1f} s), oracle/stf_ref.py fp32 + oracle/rans_oracle.c"}

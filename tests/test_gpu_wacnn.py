@@ -257,3 +257,47 @@ def test_strings_decode_with_the_cpu_oracle(model, x):
 def test_input_validation(model):
     with pytest.raises(ValueError):
         model.compress(torch.zeros(1, 3, 100, 128, device="cuda"))
+
+
+def test_config4_wacnn2_codec_at_832x1216(sd):
+    """BASELINE.json configs[3] as SURVEY.md §8d reads it: the WACNN2 codec on a 800x1216 image zero-padded to
+    832x1216 (y 320x52x76 = 1 264 640 symbols, z 192x13x19).  Too large for the CPU oracle inside a test, so the
+    size-independent properties are checked: decompress(compress(x)) == clamp(forward(x).x_hat) exactly, the strings of
+    the padded image decode on the pinned CPU coder to the symbols the GPU encoded, and cropping is the caller's job."""
+    import torch.nn.functional as F
+
+    from compressai.zoo import models
+    from oracle import coder, entropy, weights
+
+    m = models["cnn2"]()
+    assert not m.load_state_dict(sd, strict=False).unexpected_keys
+    m.update(force=True)
+    m = m.cuda().eval()
+    x = weights.seeded_image((1, 3, 800, 1216), seed=5)
+    xp = F.pad(x, (0, 0, 16, 16)).cuda()  # eval_model/__main__.py:103-115 pads to a multiple of 64, centred
+    assert xp.shape == (1, 3, 832, 1216)
+    c = m.compress(xp)
+    assert list(c["shape"]) == [13, 19]
+    d = m.decompress(c["strings"], c["shape"])
+    f = m(xp)
+    assert f["likelihoods"]["y"].shape == (1, 320, 52, 76) and f["likelihoods"]["z"].shape == (1, 192, 13, 19)
+    assert torch.equal(d["x_hat"], f["x_hat"].clamp(0, 1))
+    # the y-string is a valid reference-format stream of exactly 1 264 640 symbols: decode it on the CPU with the
+    # indexes of the GPU slice loop and re-encode
+    y, h, w = m._analysis(xp)
+    z, zh, zw = m._hyper_analysis(y, 1, h, w)
+    from compressai._native import NULL_VIEW, check, lib, stream_ptr, view_bcp
+
+    Pz = zh * zw
+    z_sym = torch.empty((1, 192 * Pz), dtype=torch.int32, device="cuda")
+    z_idx = torch.empty_like(z_sym)
+    z_hat = torch.empty((Pz, 192), dtype=torch.bfloat16, device="cuda")
+    check(lib().icm_eb_process(0, view_bcp(z, 1, 192, Pz), 1, 192, Pz, m.entropy_bottleneck.packed_params().data_ptr(), 0.0, z_sym.data_ptr(),
+                               z_idx.data_ptr(), NULL_VIEW, view_bcp(z_hat, 1, 192, Pz), NULL_VIEW, stream_ptr()))
+    ms, ss = m._hyper_synthesis(z_hat, 1, zh, zw)
+    _, sym, idx = m._slice_loop("compress", 1, h, w, ms, ss, y=y)
+    assert sym.shape[1] == 1264640
+    cdf, lengths, offsets = entropy.gc_tables()
+    got = coder.RansDecoder().decode_with_indexes(c["strings"][0][0], idx[0].cpu().numpy(), cdf, lengths, offsets)
+    assert np.array_equal(got, sym[0].cpu().numpy())
+    assert coder.rans_encode(sym[0].cpu().numpy(), idx[0].cpu().numpy(), cdf, lengths, offsets) == c["strings"][0][0]
