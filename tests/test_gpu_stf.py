@@ -163,3 +163,47 @@ def test_input_validation(model):
         model.compress(torch.zeros(1, 3, 100, 128, device="cuda"))
     with pytest.raises(ValueError):
         model.decompress([[b"\0" * 8], [b"\0" * 8, b"\0" * 8]], (2, 2))
+
+
+def test_full_size_batch_strings_equal_single_image_strings(model):
+    """BASELINE.json configs[2] semantics at the full 768x512 size: every image of a batch gets the strings it would get
+    alone (bit-exact), and the batch decodes to the per-image reconstructions."""
+    from oracle import weights
+
+    xs = torch.cat([weights.seeded_image((1, 3, 768, 512), seed=20 + s) for s in range(5)]).cuda()
+    cb = model.compress(xs)
+    assert [len(s) for s in cb["strings"]] == [5, 5] and list(cb["shape"]) == [12, 8]
+    for b in (0, 3):
+        c1 = model.compress(xs[b : b + 1])
+        assert c1["strings"][0][0] == cb["strings"][0][b] and c1["strings"][1][0] == cb["strings"][1][b]
+        d1 = model.decompress(c1["strings"], c1["shape"])
+        db = model.decompress([[cb["strings"][0][b]], [cb["strings"][1][b]]], cb["shape"])
+        assert torch.equal(d1["x_hat"], db["x_hat"])
+    d = model.decompress(cb["strings"], cb["shape"])
+    assert torch.equal(d["x_hat"], model(xs)["x_hat"].clamp(0, 1))
+    assert 608256 == 384 * 48 * 32 + 192 * 12 * 8  # symbols per image behind the Msym/s figures
+
+
+@pytest.mark.parametrize("chains,lag", [(0, 0), (2, 2), (1, 3)])
+def test_stream_pipeline_equals_plain_api(model, chains, lag):
+    """RoundTripPipeline (jobs on a pool of streams, event-chained phases, host I/O) is bit-identical to compress() +
+    decompress() on the whole batch: same byte strings, same reconstructions."""
+    from compressai.utils.pipeline import RoundTripPipeline
+    from oracle import weights
+
+    batches = [torch.cat([weights.seeded_image((1, 3, 64, 128), seed=40 + 7 * k + s) for s in range(6)]) for k in range(3)]
+    pipe = RoundTripPipeline(model, n_streams=4, part=4, decoder_streams_per_cta=4, lag=lag, chains=chains)
+    dev_batches = [b.cuda() for b in batches]
+    x_hats, none = pipe.roundtrip(dev_batches)
+    assert none is None and len(x_hats) == 3
+    pinned = [b.pin_memory() for b in batches]
+    outs = [torch.empty_like(b).pin_memory() for b in batches]
+    x_none, strings = pipe.roundtrip(pinned, host_io=True, out_host=outs)
+    torch.cuda.synchronize()
+    assert x_none is None
+    for k, xb in enumerate(dev_batches):
+        c = model.compress(xb)
+        d = model.decompress(c["strings"], c["shape"])
+        assert torch.equal(x_hats[k], d["x_hat"])
+        assert torch.equal(outs[k], d["x_hat"].cpu())
+        assert strings[k][0] == c["strings"][0] and strings[k][1] == c["strings"][1]
