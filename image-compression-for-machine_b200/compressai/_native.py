@@ -84,6 +84,9 @@ class Profile:
             Ho = (a.H + 2 * a.pad - a.KH) // a.stride + 1
             Wo = (a.W + 2 * a.pad - a.KW) // a.stride + 1
             return 2.0 * a.B * Ho * Wo * a.Cout * a.KH * a.KW * a.Cin
+        if name == "icm_swin_mlp":  # two products rows x 4C x C
+            rows, Cc = args[6], args[7]
+            return 2.0 * 2.0 * rows * 4 * Cc * Cc
         return 0.0
 
     def summary(self):
@@ -142,6 +145,7 @@ def _load():
         "icm_add_lrp": (I, [View, View, I, I, I64, View, View, P]),
         "icm_eb_process": (I, [I, View, I, I, I64, P, F, P, P, View, View, View, P]),
         "icm_conv2d": (I, [C.POINTER(ConvArgs), P]),
+        "icm_swin_mlp": (I, [P, P, P, P, P, P, I64, I, P]),
         "icm_set_conv_sm_limit": (I, [I]),
         "icm_pack_conv_weight": (I, [P, I, I, I, I, I, I, I, P, P]),
         "icm_layernorm": (I, [P, P, P, P, I, I64, I, I, I, I, I, P]),

@@ -168,8 +168,21 @@ class Engine:
                                    blk.attn.relative_position_bias_table)
         self.linear(ao, self.packed(blk.attn.proj), out=x, out_dtype=OUT_F32, residual=x)
         xn = self.layernorm(x, blk.norm2)
-        h = self.linear(xn, self.packed(blk.mlp.fc1), act=ACT_GELU)
-        self.linear(h, self.packed(blk.mlp.fc2), out=x, out_dtype=OUT_F32, residual=x)
+        self.mlp(xn, x, blk.mlp)
+        return x
+
+    fused_mlp = True  # icm_swin_mlp for C in (48, 96, 192): bit-identical to the two launches, without the hidden round trip
+
+    def mlp(self, xn, x, mlp):
+        """x += fc2(GELU(fc1(xn)))  (stf.py:34-40 with the residual of :198); x fp32 [M, C] in place, xn bf16 [M, C]."""
+        Cc = x.shape[1]
+        f1, f2 = self.packed(mlp.fc1), self.packed(mlp.fc2)
+        if self.fused_mlp and Cc in (48, 96, 192) and x.is_contiguous() and xn.is_contiguous():
+            check(lib().icm_swin_mlp(xn.data_ptr(), f1.w.data_ptr(), f1.bias.data_ptr() if f1.bias is not None else None, f2.w.data_ptr(),
+                                     f2.bias.data_ptr() if f2.bias is not None else None, x.data_ptr(), x.shape[0], Cc, stream_ptr()), "icm_swin_mlp")
+            return x
+        h = self.linear(xn, f1, act=ACT_GELU)
+        self.linear(h, f2, out=x, out_dtype=OUT_F32, residual=x)
         return x
 
     def stage(self, x, B, H, W, layer):

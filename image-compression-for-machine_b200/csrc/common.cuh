@@ -49,5 +49,7 @@ struct View {
 static inline View as_view(const icm_view &v) { return View{(char *)v.ptr, v.sb, v.sc, v.sp}; }
 
 int sm_count();
+int persistent_grid_limit();          // SMs the persistent GEMM kernels may occupy (icm_set_conv_sm_limit)
+void set_persistent_grid_limit(int n);
 
 }  // namespace icm

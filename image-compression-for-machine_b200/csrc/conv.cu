@@ -16,97 +16,9 @@
 // The K loop order (tap-major, then 64-channel chunks) is fixed and there is no split-K, so every output
 // element is reduced in the same order whatever the batch size or tile shape: the encoder and decoder
 // sides of the codec see bit-identical means/scales (SURVEY.md §7 "Encoder/decoder determinism").
-#include "common.cuh"
-
-#include <cuda.h>
+#include "umma.cuh"
 
 namespace icm {
-
-constexpr int BM = 128;      // pixels per tile == TMEM lanes
-constexpr int BK = 64;       // bf16 channels per k-step == one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int MAX_STAGES = 8;
-
-// ---------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{ // implies tcgen05.fence::before_thread_sync
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
-// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 struct ConvParams {
     int Ho, Wo;            // output spatial size
@@ -126,23 +38,6 @@ struct ConvParams {
     const void *residual;
     void *out;
 };
-
-// erf-GELU v * Phi(v) as v * sigmoid(P(v)), P an odd minimax polynomial of min(max(v, -5), 5): |error| <= 2.6e-5
-// absolute over all v (fitted against 0.5 v (1 + erf(v / sqrt 2)); the tanh form is 10x worse), a sixteenth of the
-// bf16 rounding of a stored activation of magnitude 0.1.  10 instructions (2 MUFU) per element; the
-// Abramowitz-Stegun 7.1.26 form used before took 16.5 and libdevice erff ~30, and the epilogue of the GELU linears
-// is instruction-issue-bound (~20 instructions per output against a budget of 14 at the HBM roofline).
-__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-__device__ __forceinline__ float gelu_erf(float v)
-{
-    const float c = fminf(fmaxf(v, -5.0f), 5.0f);
-    const float c2 = c * c;
-    float p = fmaf(0.0010142815299332142f, c2, -0.10677584260702133f); // coefficients pre-multiplied by -log2(e)
-    p = fmaf(p, c2, -2.301121234893799f);
-    return v * mufu_rcp(1.0f + mufu_ex2(p * c));
-}
 
 // The activation switch sits OUTSIDE the 16-element loop (one uniform branch per chunk): with it inside, the
 // unrolled epilogue carried every activation's code and a branch chain per element (~32 instructions per
@@ -177,11 +72,6 @@ __device__ __forceinline__ void apply_act16(float (&v)[16], int act)
 
 constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
 constexpr int CONV_THREADS = (2 + EPI_WARPS) * 32; // TMA warp + MMA warp + epilogue warps
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA pipeline runs
 // across tile boundaries, and the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps
@@ -463,22 +353,6 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, int Cout, int Ci
 }
 
 // ------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 static int pick_tile_w_log2(int Ho, int Wo)
 {
     long long best = -1;
@@ -491,7 +365,6 @@ static int pick_tile_w_log2(int Ho, int Wo)
     return best_l;
 }
 
-static thread_local int g_sm_limit = 0;
 
 }  // namespace icm
 
@@ -504,7 +377,7 @@ using namespace icm;
 extern "C" int icm_set_conv_sm_limit(int n_sms)
 {
     ICM_CHECK_ARG(n_sms >= 0, "icm_set_conv_sm_limit: negative limit");
-    g_sm_limit = n_sms;
+    set_persistent_grid_limit(n_sms);
     return ICM_OK;
 }
 
@@ -601,8 +474,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.total_tiles = (int)(m_tiles * p.n_tiles);
     auto magic = [](int d) -> unsigned long long { return d <= 1 ? 0ull : ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; };
     p.fd_n = magic(p.n_tiles); p.fd_w = magic(p.tiles_w); p.fd_h = magic(p.tiles_h);
-    int max_ctas = sm_count();
-    if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
+    const int max_ctas = persistent_grid_limit();
     const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
     conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
     ICM_LAUNCH_CHECK();

@@ -38,6 +38,15 @@ int sm_count()
     return cached;
 }
 
+static thread_local int g_persistent_sm_limit = 0;
+int persistent_grid_limit()
+{
+    const int n = sm_count();
+    return (g_persistent_sm_limit > 0 && g_persistent_sm_limit < n) ? g_persistent_sm_limit : n;
+}
+void set_persistent_grid_limit(int n) { g_persistent_sm_limit = n; }
+
+
 }  // namespace icm
 
 extern "C" const char *icm_last_error(void) { return icm::g_error; }

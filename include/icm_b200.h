@@ -175,8 +175,14 @@ typedef struct {
     int res_mode;          /* 0: out = act(acc) + res   1: out = act(acc + res)   2: out = act(acc) * res */
 } icm_conv_args;
 int icm_conv2d(const icm_conv_args *a, void *stream);
-/* Cap on the SMs icm_conv2d occupies (0 = all), for overlap with the rANS coders on another stream. */
+/* Cap on the SMs icm_conv2d / icm_swin_mlp occupy (0 = all), for overlap with the rANS coders on another stream. */
 int icm_set_conv_sm_limit(int n_sms);
+/* Fused Swin MLP (stf.py:34-40 inside :194-198): x[row] += fc2(GELU(fc1(h[row]))), h = LayerNorm2(x) in bf16 [rows, C],
+ * x the fp32 residual stream [rows, C] updated in place; w1 / w2 packed by icm_pack_conv_weight ([4C][ceil64(C)] and
+ * [C][4C]).  C in {48, 96, 192}; the 4C-wide hidden activation stays in shared memory / TMEM.  Bit-identical to two
+ * icm_conv2d launches (ICM_ACT_GELU, then residual). */
+int icm_swin_mlp(const void *d_h_bf16, const void *d_w1_packed, const float *d_b1, const void *d_w2_packed, const float *d_b2,
+                 float *d_x, int64_t rows, int C, void *stream);
 int icm_pack_conv_weight(const float *d_w_oihw, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,
                          int pixel_shuffle, void *d_out_bf16, void *stream);
 

@@ -169,3 +169,32 @@ def test_patch_embed_and_final_conv(eng):
         cw3, cb3 = c(w3), c(b3)
         check(lib().icm_final_conv(xin.data_ptr(), cw3.data_ptr(), cb3.data_ptr(), o.data_ptr(), B, H, W, 48, clamp, stream_ptr()))
         _close(o, ref.clamp(0, 1) if clamp else ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("C,M", [(48, 1000), (96, 777), (192, 4096 + 57), (48, 128 * 300 + 5)])
+def test_fused_swin_mlp_is_bit_identical_to_two_launches(eng, C, M):
+    """icm_swin_mlp (hidden activation kept on chip) == fc1 + GELU launch followed by fc2 + residual launch, bit for bit
+    (same K order, same rounding points), and close to the fp32 PyTorch MLP."""
+    from compressai.models._engine import PackedConv  # noqa: F401
+
+    g = torch.Generator().manual_seed(C + M)
+    mlp = torch.nn.Module()
+    mlp.fc1 = torch.nn.Linear(C, 4 * C)
+    mlp.fc2 = torch.nn.Linear(4 * C, C)
+    with torch.no_grad():
+        for prm in mlp.parameters():
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.1 if prm.dim() == 1 else 1.0 / prm.shape[1] ** 0.5))
+    mlp = mlp.cuda()
+    x0 = torch.randn(M, C, generator=g) * 2
+    xn = (torch.randn(M, C, generator=g) * 1.5).cuda().bfloat16()
+    xa, xb = x0.cuda().clone(), x0.cuda().clone()
+    eng.fused_mlp = True
+    eng.mlp(xn, xa, mlp)
+    eng.fused_mlp = False
+    eng.mlp(xn, xb, mlp)
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb), float((xa - xb).abs().max())
+    with torch.no_grad():
+        h = F.gelu(F.linear(xn.float().cpu(), _bf(mlp.fc1.weight.cpu()), mlp.fc1.bias.cpu()))
+        ref = x0 + F.linear(_bf(h), _bf(mlp.fc2.weight.cpu()), mlp.fc2.bias.cpu())
+    _close(xa, ref, rtol=5e-3, atol=5e-3)
