@@ -164,10 +164,10 @@ def main():
     ap.add_argument("--weights", default="default", choices=sorted(WEIGHTS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=10, help="CUDA streams of the codec pipeline")
+    ap.add_argument("--streams", type=int, default=12, help="CUDA streams of the codec pipeline")
     ap.add_argument("--part", type=int, default=32, help="images per pipeline job")
     ap.add_argument("--dec-per-cta", type=int, default=8, help="rANS decoder streams per CTA in the pipeline (1, 2, 4, 8, 16)")
-    ap.add_argument("--lag", type=int, default=6, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag")
+    ap.add_argument("--lag", type=int, default=8, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag")
     ap.add_argument("--chains", type=int, default=2, help="pipeline: jobs allowed in a throughput-bound phase at once (0 = unordered)")
     ap.add_argument("--conv-sms", type=int, default=-1, help="cap on SMs used by the conv kernel (0 = all, -1 = automatic)")
     args = ap.parse_args()

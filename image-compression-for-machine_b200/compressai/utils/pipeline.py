@@ -32,7 +32,7 @@ class RoundTripPipeline:
     up to `lag` other jobs run beside them.  Without the chain all jobs start in lockstep, reach their coders
     together and leave the GPU idle (measured run-to-run spread 400-530 images/s)."""
 
-    def __init__(self, model, n_streams=10, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=6, chains=2):
+    def __init__(self, model, n_streams=12, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=8, chains=2):
         self.model = model
         self.decoder_streams_per_cta = int(decoder_streams_per_cta)
         # The decoder's CTAs (~155 KB of shared memory) cannot share an SM with a persistent conv CTA (~200 KB); the
@@ -60,12 +60,14 @@ class RoundTripPipeline:
             self._decoders[key] = (ans.StreamDecoder(n), ans.StreamDecoder(n))
         return self._decoders[key]
 
-    def _pin(self, key, shape, dtype):
-        t = self._pinned.get(key)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype).pin_memory()
-            self._pinned[key] = t
-        return t
+    def _pin(self, shape, dtype):
+        """A pinned staging buffer from the pool (returned by _unpin once its job's strings have been built)."""
+        free = self._pinned.setdefault((tuple(shape), dtype), [])
+        return free.pop() if free else torch.empty(shape, dtype=dtype).pin_memory()
+
+    def _unpin(self, *bufs):
+        for t in bufs:
+            self._pinned[(tuple(t.shape), t.dtype)].append(t)
 
     def _phase(self, chain):
         """begin: wait for the chain's token; end: pass it on."""
@@ -124,15 +126,15 @@ class RoundTripPipeline:
                 zh, zw = c["shape"]
                 y_str, z_str = c["y"], c["z"]
                 if host_io:  # streams leave for the host and come back, like bytes handed to a decoder
-                    hy = self._pin(("y", bi, lo), y_str[0].shape, torch.uint8)
-                    hz = self._pin(("z", bi, lo), z_str[0].shape, torch.uint8)
-                    hsy = self._pin(("sy", bi, lo), y_str[1].shape, torch.int32)
-                    hsz = self._pin(("sz", bi, lo), z_str[1].shape, torch.int32)
+                    hy, hz = self._pin(y_str[0].shape, torch.uint8), self._pin(z_str[0].shape, torch.uint8)
+                    hsy, hsz = self._pin(y_str[1].shape, torch.int32), self._pin(z_str[1].shape, torch.int32)
                     hy.copy_(y_str[0], non_blocking=True); hz.copy_(z_str[0], non_blocking=True)
                     hsy.copy_(y_str[1], non_blocking=True); hsz.copy_(z_str[1], non_blocking=True)
                     y_str = (hy.to(dev, non_blocking=True), hsy.to(dev, non_blocking=True))
                     z_str = (hz.to(dev, non_blocking=True), hsz.to(dev, non_blocking=True))
-                    pending.append((bi, lo, hi, hy, hsy, hz, hsz))
+                    ev = torch.cuda.Event()
+                    ev.record(self._streams[slot])  # both directions of the staging buffers are done after this
+                    pending.append((ev, bi, hy, hsy, hz, hsz))
                 y_hat, _ = m._decode_part(y_str, z_str, hi - lo, zh, zw, True, decoders=self._decoder_pair(slot, hi - lo))
                 decoded[t] = (y_hat, zh, zw)
 
@@ -151,14 +153,35 @@ class RoundTripPipeline:
                 if keep_outputs and out_host is None:
                     results[bi].append(x_hat)
 
+        strings = [[[], []] for _ in batches] if host_io else None
+
+        def drain(block):
+            """Build the Python byte strings of finished jobs (in job order) while the GPU works on later ones."""
+            while pending and (block or pending[0][0].query()):
+                ev, bi, hy, hsy, hz, hsz = pending.pop(0)
+                ev.synchronize()
+                for packed, sizes, dst in ((hy, hsy, strings[bi][0]), (hz, hsz, strings[bi][1])):
+                    hs = sizes.tolist()
+                    if min(hs[:-1]) < 0:
+                        raise RuntimeError("rANS encoder reported an error status (buffer capacity or bad index)")
+                    raw, o = packed.numpy(), 0
+                    for v in hs[:-1]:
+                        dst.append(raw[o:o + v].tobytes())
+                        o += v
+                self._unpin(hy, hsy, hz, hsz)
+
         try:
             for t in range(len(jobs) + lag):
                 if t < len(jobs):
                     front(t)
                 if t - lag >= 0:
                     back(t - lag)
+                if host_io:
+                    drain(False)
             for st in self._streams:
                 cur.wait_stream(st)
+            if host_io:
+                drain(True)
         finally:
             check(lib().icm_set_conv_sm_limit(0), "icm_set_conv_sm_limit")
             check(lib().icm_set_decoder_streams_per_cta(0), "icm_set_decoder_streams_per_cta")
@@ -169,17 +192,6 @@ class RoundTripPipeline:
                 for t in parts:
                     t.record_stream(cur)
                 x_hats.append(parts[0] if len(parts) == 1 else torch.cat(parts, 0))
-        strings = None
         if host_io:
-            cur.synchronize()
-            strings = [[[], []] for _ in batches]
-            for bi, lo, hi, hy, hsy, hz, hsz in pending:
-                for packed, sizes, dst in ((hy, hsy, strings[bi][0]), (hz, hsz, strings[bi][1])):
-                    hs = sizes.tolist()
-                    if min(hs[:-1]) < 0:
-                        raise RuntimeError("rANS encoder reported an error status (buffer capacity or bad index)")
-                    raw, o = packed.numpy(), 0
-                    for v in hs[:-1]:
-                        dst.append(raw[o:o + v].tobytes())
-                        o += v
+            cur.synchronize()  # x_hat copies into out_host have landed
         return x_hats, strings
