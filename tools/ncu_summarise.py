@@ -52,7 +52,7 @@ def main():
         grid = r[col["Grid Size"]] if "Grid Size" in col else ""
         pending.append((name, grid, us, db, dp, tp, sp, regs))
     # assign rows to keys in order: every key owns >= 1 consecutive rows; split by expected kernel names
-    owner = {"icm_conv2d": ["conv_igemm_kernel"], "icm_rans_encode_batch": ["rans_records_kernel", "rans_encode_kernel", "rans_scan_kernel", "rans_pack_kernel"]}
+    owner = {"icm_conv2d": ["conv_igemm_kernel"], "icm_swin_mlp": ["swin_mlp_kernel"], "icm_rans_encode_batch": ["rans_records_kernel", "rans_encode_kernel", "rans_scan_kernel", "rans_pack_kernel"]}
     pi = 0
     for k in keys:
         entry = k["key"][0]
