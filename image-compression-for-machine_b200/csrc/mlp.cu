@@ -21,17 +21,19 @@ namespace icm {
 constexpr int MLP_EPI_WARPS = 16;
 constexpr int MLP_THREADS = (2 + MLP_EPI_WARPS) * 32;
 constexpr int HC = 64; // hidden columns per chunk == one swizzle row of the second product's A operand
+constexpr int MAX_RING = 8;
 
 struct MlpParams {
     long long M;
     int C, k1_chunks, n_hc, tiles; // k1_chunks = ceil(C / 64), n_hc = 4C / 64
     int tmem_cols, bias_in_smem; // C = 192 has no shared memory left for the biases: read through L1 instead
+    int ring, a1_bufs;           // depth of the W1 / W2 rings; h-tile buffers (2, or 1 when shared memory is short)
     const float *b1, *b2;
     float *x;
 };
 
 struct alignas(16) MlpBars {
-    uint64_t a1_full[2], a1_empty[2], w1_full[2], w1_empty[2], w2_full[2], w2_empty[2];
+    uint64_t a1_full[2], a1_empty[2], w1_full[MAX_RING], w1_empty[MAX_RING], w2_full[MAX_RING], w2_empty[MAX_RING];
     uint64_t d1_full[2], d1_empty[2], a2_full[2], a2_empty[2], d2_full, d2_empty;
     uint32_t tmem_slot, pad;
 };
@@ -46,7 +48,7 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
     const uint32_t w1_bytes = (uint32_t)p.k1_chunks * (HC * 128);    // W1 block: [64 hidden rows x C]
     const uint32_t w2_bytes = (((uint32_t)p.C * 128) + 1023) & ~1023u; // W2 block: [C rows x 64 hidden]
     const uint32_t a2_bytes = BM * 128;                              // GELU chunk [128 x 64]
-    unsigned char *a1 = base, *w1 = a1 + 2 * a1_bytes, *w2 = w1 + 2 * w1_bytes, *a2 = w2 + 2 * w2_bytes;
+    unsigned char *a1 = base, *w1 = a1 + p.a1_bufs * a1_bytes, *w2 = w1 + p.ring * w1_bytes, *a2 = w2 + p.ring * w2_bytes;
     MlpBars *bar = reinterpret_cast<MlpBars *>(a2 + 2 * a2_bytes);
     float *s_b1 = reinterpret_cast<float *>(bar + 1), *s_b2 = s_b1 + 4 * p.C;
 
@@ -54,10 +56,12 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar->a1_full[i], 1); mbar_init(&bar->a1_empty[i], 1);
-            mbar_init(&bar->w1_full[i], 1); mbar_init(&bar->w1_empty[i], 1);
-            mbar_init(&bar->w2_full[i], 1); mbar_init(&bar->w2_empty[i], 1);
             mbar_init(&bar->d1_full[i], 1); mbar_init(&bar->d1_empty[i], MLP_EPI_WARPS);
             mbar_init(&bar->a2_full[i], MLP_EPI_WARPS); mbar_init(&bar->a2_empty[i], 1);
+        }
+        for (int i = 0; i < MAX_RING; ++i) {
+            mbar_init(&bar->w1_full[i], 1); mbar_init(&bar->w1_empty[i], 1);
+            mbar_init(&bar->w2_full[i], 1); mbar_init(&bar->w2_empty[i], 1);
         }
         mbar_init(&bar->d2_full, 1); mbar_init(&bar->d2_empty, MLP_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -89,15 +93,18 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                 for (int kc = 0; kc < p.k1_chunks; ++kc)
                     tma_load_2d(&map_h, &bar->a1_full[slot], a1 + slot * a1_bytes + kc * (BM * 128), kc * 64, tile * BM);
             };
-            int it = 0;          // tiles done by this CTA
-            uint32_t wcount = 0; // weight blocks issued (ring slot = wcount & 1, parity = (wcount >> 1) & 1)
+            int it = 0;                      // tiles done by this CTA
+            int ws = 0;                      // weight ring slot and its phase
+            uint32_t wpar = 0;
+            const int ab = p.a1_bufs;        // h tile t lives in buffer t % ab, phase (t / ab) & 1
             if ((int)blockIdx.x < p.tiles) load_h(blockIdx.x, 0, 0);
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
                 const int next = tile + gridDim.x;
-                if (next < p.tiles) load_h(next, (it + 1) & 1, (uint32_t)(((it + 1) >> 1) & 1)); // prefetch the next h tile
-                for (int j = 0; j < p.n_hc; ++j, ++wcount) {
-                    const int s = wcount & 1;
-                    const uint32_t par = (wcount >> 1) & 1;
+                if (ab == 2 && next < p.tiles) load_h(next, (it + 1) & 1, (uint32_t)(((it + 1) >> 1) & 1)); // prefetch the next h tile
+                for (int j = 0; j < p.n_hc; ++j) {
+                    const int s = ws;
+                    const uint32_t par = wpar;
+                    if (++ws == p.ring) { ws = 0; wpar ^= 1; }
                     mbar_wait(&bar->w1_empty[s], par ^ 1);
                     mbar_expect_tx(&bar->w1_full[s], w1_bytes);
                     for (int kc = 0; kc < p.k1_chunks; ++kc)
@@ -106,6 +113,8 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                     mbar_expect_tx(&bar->w2_full[s], (uint32_t)p.C * 128);
                     tma_load_2d(&map_w2, &bar->w2_full[s], w2 + s * w2_bytes, j * HC, 0);
                 }
+                // single h buffer: the next tile's h can only be requested once every GEMM1 of this tile has read it
+                if (ab == 1 && next < p.tiles) load_h(next, 0, (uint32_t)((it + 1) & 1));
             }
         }
     } else if (warp == 1) {
@@ -113,62 +122,126 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
         const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HC >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         int it = 0;
-        uint32_t c1 = 0, c2 = 0; // chunks issued to GEMM1 / GEMM2 over the whole kernel
+        uint32_t c1 = 0, c2 = 0; // chunks issued to GEMM1 / GEMM2 over the whole kernel (D1 / A2 buffer = count & 1)
+        int r1 = 0, r2 = 0;      // W1 / W2 ring slots and phases
+        uint32_t rp1 = 0, rp2 = 0;
         auto gemm1 = [&](int slot_a, bool last) {
             const int s = c1 & 1;
             const uint32_t par = (c1 >> 1) & 1;
-            mbar_wait(&bar->w1_full[s], par);
-            mbar_wait(&bar->d1_empty[s], par ^ 1); // D1 buffer == ring slot index (both advance once per chunk)
+            mbar_wait(&bar->w1_full[r1], rp1);
+            mbar_wait(&bar->d1_empty[s], par ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint32_t d = tmem_base + (uint32_t)s * HC;
                 for (int kc = 0; kc < p.k1_chunks; ++kc) {
                     const uint64_t da = make_smem_desc(smem_u32(a1 + slot_a * a1_bytes + kc * (BM * 128)));
-                    const uint64_t db = make_smem_desc(smem_u32(w1 + s * w1_bytes + kc * (HC * 128)));
+                    const uint64_t db = make_smem_desc(smem_u32(w1 + r1 * w1_bytes + kc * (HC * 128)));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kc | k) != 0);
                 }
-                umma_commit(&bar->w1_empty[s]);
+                umma_commit(&bar->w1_empty[r1]);
                 umma_commit(&bar->d1_full[s]);
                 if (last) umma_commit(&bar->a1_empty[slot_a]); // every GEMM1 of this tile has read the h tile
             }
             __syncwarp();
             ++c1;
+            if (++r1 == p.ring) { r1 = 0; rp1 ^= 1; }
         };
         auto gemm2 = [&](bool first, bool last) {
             const int s = c2 & 1;
             const uint32_t par = (c2 >> 1) & 1;
             mbar_wait(&bar->a2_full[s], par);
-            mbar_wait(&bar->w2_full[s], par);
+            mbar_wait(&bar->w2_full[r2], rp2);
             if (first) mbar_wait(&bar->d2_empty, (uint32_t)((it & 1) ^ 1)); // epilogue 2 of the previous tile has drained D2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
-                const uint64_t da = make_smem_desc(smem_u32(a2 + s * a2_bytes)), db = make_smem_desc(smem_u32(w2 + s * w2_bytes));
+                const uint64_t da = make_smem_desc(smem_u32(a2 + s * a2_bytes)), db = make_smem_desc(smem_u32(w2 + r2 * w2_bytes));
 #pragma unroll
                 for (int k = 0; k < HC / UMMA_K; ++k) umma_bf16(tmem_base + d2_col, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (!first) || k != 0);
                 umma_commit(&bar->a2_empty[s]);
-                umma_commit(&bar->w2_empty[s]);
+                umma_commit(&bar->w2_empty[r2]);
                 if (last) umma_commit(&bar->d2_full);
             }
             __syncwarp();
             ++c2;
+            if (++r2 == p.ring) { r2 = 0; rp2 ^= 1; }
         };
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-            const int slot_a = it & 1;
-            mbar_wait(&bar->a1_full[slot_a], (uint32_t)((it >> 1) & 1));
-            for (int j = 0; j < p.n_hc; ++j) {
-                gemm1(slot_a, j == p.n_hc - 1);
-                if (j > 0) gemm2(j == 1, false);
+        // One continuous chunk stream across tiles: GEMM1 of a chunk is always issued before GEMM2 of the previous chunk,
+        // also when the two belong to different tiles -- otherwise the first GEMM1 of a tile waited for the last GELU chunk
+        // of the tile before, and the 16 epilogue warps idled for a full MMA round trip once per tile.
+        int n_my = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) ++n_my;
+        const long long total = (long long)n_my * p.n_hc;
+        int j1 = 0, t1 = 0; // chunk / tile ordinal of the next GEMM1
+        int j2 = 0;         // chunk of the next GEMM2 (its tile ordinal is `it`, used for the D2 hand-shake)
+        for (long long g = 0; g <= total; ++g) {
+            if (g < total) {
+                const int slot_a = p.a1_bufs == 2 ? (t1 & 1) : 0;
+                if (j1 == 0) mbar_wait(&bar->a1_full[slot_a], (uint32_t)(p.a1_bufs == 2 ? ((t1 >> 1) & 1) : (t1 & 1)));
+                gemm1(slot_a, j1 == p.n_hc - 1);
+                if (++j1 == p.n_hc) { j1 = 0; ++t1; }
             }
-            gemm2(p.n_hc == 1, true);
+            if (g > 0) {
+                gemm2(j2 == 0, j2 == p.n_hc - 1);
+                if (++j2 == p.n_hc) { j2 = 0; ++it; }
+            }
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;          // TMEM lane quarter
         const int grp = (warp - 2) >> 2; // 16-column group of a 64-column chunk
         const int r = q * 32 + lane;     // row of the tile
-        int it = 0;
+        int it = 0, prev_tile = -1;
         uint32_t ce = 0; // chunks finished
+        // epilogue 2: output tile + bias + residual, in place.  It runs one chunk late -- after the first GELU chunk of the NEXT
+        // tile -- so that the last GEMM2 of its own tile completes behind useful work instead of in front of a stalled epilogue.
+        auto epilogue2 = [&](int tile2, int it2) {
+            mbar_wait(&bar->d2_full, (uint32_t)(it2 & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long grow = (long long)tile2 * BM + r;
+            const int n_c16 = p.C / 16;
+            uint32_t acc[16];
+            bool have = false;
+            if (grp < n_c16) { tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + d2_col + (uint32_t)(grp * 16), acc); have = true; }
+            // C <= 192: at most three chunks per warp (grp, grp + 4, grp + 8); loads of later chunks are issued one ahead
+            for (int c16 = grp; c16 < n_c16; c16 += 4) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(acc[k]);
+                if (c16 + 4 < n_c16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + d2_col + (uint32_t)((c16 + 4) * 16), acc);
+                else {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar->d2_empty);
+                }
+                if (grow < p.M) {
+                    float *xp = p.x + grow * p.C + c16 * 16;
+                    const float4 *bp = reinterpret_cast<const float4 *>(b2p + c16 * 16);
+                    float rv[16];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(rv[8 * k]), "=f"(rv[8 * k + 1]), "=f"(rv[8 * k + 2]),
+                                     "=f"(rv[8 * k + 3]), "=f"(rv[8 * k + 4]), "=f"(rv[8 * k + 5]), "=f"(rv[8 * k + 6]), "=f"(rv[8 * k + 7]) : "l"(xp + 8 * k));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 t = bp[k];
+                        v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] += rv[k]; // same order as conv.cu: (acc + bias) + residual
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(xp + 8 * k), "f"(v[8 * k]), "f"(v[8 * k + 1]),
+                                     "f"(v[8 * k + 2]), "f"(v[8 * k + 3]), "f"(v[8 * k + 4]), "f"(v[8 * k + 5]), "f"(v[8 * k + 6]), "f"(v[8 * k + 7]) : "memory");
+                }
+            }
+            if (!have) { // a warp without a chunk of the output tile still owes its arrival
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar->d2_empty);
+            }
+        };
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
             {   // epilogue 2 reads this thread's residual row once per tile: ask L2 for it now (ncu: a quarter of the stall
                 // samples sat on those loads with their full HBM latency exposed)
@@ -215,54 +288,11 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the MMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar->a2_full[s]);
+                if (j == 0 && prev_tile >= 0) epilogue2(prev_tile, it - 1);
             }
-            // epilogue 2: output tile + bias + residual, in place
-            mbar_wait(&bar->d2_full, (uint32_t)(it & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long grow = (long long)tile * BM + r;
-            const int n_c16 = p.C / 16;
-            uint32_t acc[16];
-            bool have = false;
-            if (grp < n_c16) { tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + d2_col + (uint32_t)(grp * 16), acc); have = true; }
-            // C <= 192: at most three chunks per warp (grp, grp + 4, grp + 8); loads of later chunks are issued one ahead
-            for (int c16 = grp; c16 < n_c16; c16 += 4) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float v[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(acc[k]);
-                if (c16 + 4 < n_c16) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + d2_col + (uint32_t)((c16 + 4) * 16), acc);
-                else {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar->d2_empty);
-                }
-                if (grow < p.M) {
-                    float *xp = p.x + grow * p.C + c16 * 16;
-                    const float4 *bp = reinterpret_cast<const float4 *>(b2p + c16 * 16);
-                    float rv[16];
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(rv[8 * k]), "=f"(rv[8 * k + 1]), "=f"(rv[8 * k + 2]),
-                                     "=f"(rv[8 * k + 3]), "=f"(rv[8 * k + 4]), "=f"(rv[8 * k + 5]), "=f"(rv[8 * k + 6]), "=f"(rv[8 * k + 7]) : "l"(xp + 8 * k));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float4 t = bp[k];
-                        v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] += rv[k]; // same order as conv.cu: (acc + bias) + residual
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(xp + 8 * k), "f"(v[8 * k]), "f"(v[8 * k + 1]),
-                                     "f"(v[8 * k + 2]), "f"(v[8 * k + 3]), "f"(v[8 * k + 4]), "f"(v[8 * k + 5]), "f"(v[8 * k + 6]), "f"(v[8 * k + 7]) : "memory");
-                }
-            }
-            if (!have) { // a warp without a chunk of the output tile still owes its arrival
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar->d2_empty);
-            }
+            prev_tile = tile;
         }
+        if (prev_tile >= 0) epilogue2(prev_tile, it - 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -323,8 +353,17 @@ extern "C" int icm_swin_mlp(const void *d_h_bf16, const void *d_w1_packed, const
     }
     const size_t a1_bytes = (size_t)p.k1_chunks * (BM * 128), w1_bytes = (size_t)p.k1_chunks * (HC * 128);
     const size_t w2_bytes = (((size_t)C * 128) + 1023) & ~(size_t)1023, a2_bytes = BM * 128;
-    size_t smem_bytes = 1024 + 2 * (a1_bytes + w1_bytes + w2_bytes + a2_bytes) + sizeof(MlpBars) + 16;
-    p.bias_in_smem = smem_bytes + (size_t)5 * C * 4 <= 227 * 1024;
+    // The weight blocks of a chunk are used once and re-fetched from L2 for every tile; with a 2-slot ring that ~1.4 us
+    // TMA round trip sat on the critical path of every second chunk (2 700 cycles per chunk measured against a 1 000-cycle
+    // GELU bound).  The rings are as deep as shared memory allows; at C = 192 the h tile gives up its second buffer.
+    const size_t budget = 227 * 1024, fixed = 1024 + 2 * a2_bytes + sizeof(MlpBars) + 16;
+    p.a1_bufs = 2;
+    p.ring = (int)((budget - fixed - 2 * a1_bytes) / (w1_bytes + w2_bytes));
+    if (p.ring < 3) { p.a1_bufs = 1; p.ring = (int)((budget - fixed - a1_bytes) / (w1_bytes + w2_bytes)); }
+    if (p.ring > MAX_RING) p.ring = MAX_RING;
+    ICM_CHECK_ARG(p.ring >= 2, "icm_swin_mlp: shared memory budget exceeded");
+    size_t smem_bytes = fixed + p.a1_bufs * a1_bytes + (size_t)p.ring * (w1_bytes + w2_bytes);
+    p.bias_in_smem = smem_bytes + (size_t)5 * C * 4 <= budget;
     if (p.bias_in_smem) smem_bytes += (size_t)5 * C * 4;
     ICM_CHECK_ARG(smem_bytes <= 227 * 1024, "icm_swin_mlp: shared memory budget exceeded (%zu bytes)", smem_bytes);
     static thread_local bool configured = false;
