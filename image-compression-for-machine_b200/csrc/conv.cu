@@ -151,20 +151,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ------------------------------------------------------------------ MMA issuer
         // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            mbar_wait(&acc_empty[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
-            for (int it = 0; it < k_iters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+        // ONE thread runs the whole issue loop (waits included), and the shared-memory descriptors advance by addition:
+        // a clock64 timeline showed ~130 cycles of single-thread overhead per tcgen05.mma and ~150 per mbarrier wait with a
+        // per-iteration elect / reconvergence and the descriptor rebuilt from the address each k-step -- more than the
+        // MMAs themselves take for N <= 176, which is why those layers sat at 30-70 % of the tensor peak.
+        if (elect_one()) {
+            const uint64_t desc0 = make_smem_desc(smem_u32(tiles));
+            const uint64_t step = (uint64_t)(stage_bytes >> 4), boff = (uint64_t)(a_bytes >> 4); // in the 16-byte address field
+            uint64_t da = desc0;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t db = da + boff;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the 16-byte address field
@@ -172,12 +178,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
                     if (it == k_iters - 1) umma_commit(&acc_full[acc]); // accumulator complete
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; da = desc0; } else da += step;
                 }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..17)
         const int q = warp & 3;           // TMEM lane quarter this warp may read

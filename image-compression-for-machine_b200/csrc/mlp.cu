@@ -119,6 +119,8 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        // (one thread runs the whole role, waits included: no per-call elect / reconvergence)
+        if (elect_one()) {
         const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HC >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         int it = 0;
@@ -131,7 +133,7 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
             mbar_wait(&bar->w1_full[r1], rp1);
             mbar_wait(&bar->d1_empty[s], par ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
+            {
                 const uint32_t d = tmem_base + (uint32_t)s * HC;
                 for (int kc = 0; kc < p.k1_chunks; ++kc) {
                     const uint64_t da = make_smem_desc(smem_u32(a1 + slot_a * a1_bytes + kc * (BM * 128)));
@@ -143,7 +145,6 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                 umma_commit(&bar->d1_full[s]);
                 if (last) umma_commit(&bar->a1_empty[slot_a]); // every GEMM1 of this tile has read the h tile
             }
-            __syncwarp();
             ++c1;
             if (++r1 == p.ring) { r1 = 0; rp1 ^= 1; }
         };
@@ -154,7 +155,7 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
             mbar_wait(&bar->w2_full[r2], rp2);
             if (first) mbar_wait(&bar->d2_empty, (uint32_t)((it & 1) ^ 1)); // epilogue 2 of the previous tile has drained D2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
+            {
                 const uint64_t da = make_smem_desc(smem_u32(a2 + s * a2_bytes)), db = make_smem_desc(smem_u32(w2 + r2 * w2_bytes));
 #pragma unroll
                 for (int k = 0; k < HC / UMMA_K; ++k) umma_bf16(tmem_base + d2_col, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (!first) || k != 0);
@@ -162,7 +163,6 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                 umma_commit(&bar->w2_empty[r2]);
                 if (last) umma_commit(&bar->d2_full);
             }
-            __syncwarp();
             ++c2;
             if (++r2 == p.ring) { r2 = 0; rp2 ^= 1; }
         };
@@ -186,6 +186,8 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                 if (++j2 == p.n_hc) { j2 = 0; ++it; }
             }
         }
+        }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;          // TMEM lane quarter
