@@ -25,6 +25,7 @@ struct ConvParams {
     int TW_log2;           // tile = TW x TH pixels, TW * TH == 128
     int tiles_w, tiles_h;
     int k_chunks;          // ceil(Cin / 64)
+    int last_k16;          // K = 16 steps that hold real channels in the last 64-channel chunk of a tap (1..4)
     int Cin_pad;           // channels per tap in the packed weight
     int KH, KW, stride, pad;
     int BN, Cout, stages, tmem_cols; // tmem_cols = two accumulators
@@ -167,14 +168,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
+                int chunk = 0;
                 for (int it = 0; it < k_iters; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t db = da + boff;
+                    // the channels beyond Cin in a tap's last chunk are zero in both operands (TMA fill, weight padding):
+                    // their K = 16 steps are skipped, which is exact (Cin = 224: 14 instead of 16 MMAs per tap)
+                    const int n_k = (chunk == p.k_chunks - 1) ? p.last_k16 : BK / UMMA_K;
+                    if (++chunk == p.k_chunks) chunk = 0;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in the 16-byte address field
-                        umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                        if (k < n_k) umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
                     if (it == k_iters - 1) umma_commit(&acc_full[acc]); // accumulator complete
@@ -412,6 +418,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     const int Cin = a->Cin; // channels actually read; the packed weight pads each tap to a multiple of 64
     p.k_chunks = (Cin + BK - 1) / BK;
     p.Cin_pad = p.k_chunks * BK;
+    p.last_k16 = (Cin - (p.k_chunks - 1) * BK + UMMA_K - 1) / UMMA_K;
     p.KH = a->KH; p.KW = a->KW; p.stride = a->stride; p.pad = a->pad;
     p.Cout = a->Cout;
     const int n_tiles = (a->Cout + 255) / 256;

@@ -138,8 +138,10 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant
                 for (int kc = 0; kc < p.k1_chunks; ++kc) {
                     const uint64_t da = make_smem_desc(smem_u32(a1 + slot_a * a1_bytes + kc * (BM * 128)));
                     const uint64_t db = make_smem_desc(smem_u32(w1 + r1 * w1_bytes + kc * (HC * 128)));
+                    const int n_k = (kc == p.k1_chunks - 1) ? (p.C - kc * 64 + UMMA_K - 1) / UMMA_K : BK / UMMA_K; // skip all-zero K steps
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kc | k) != 0);
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        if (k < n_k) umma_bf16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kc | k) != 0);
                 }
                 umma_commit(&bar->w1_empty[r1]);
                 umma_commit(&bar->d1_full[s]);
