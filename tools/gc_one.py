@@ -1,0 +1,51 @@
+"""Back-to-back timing of the quantise / LRP-add entropy kernels at the benchmark slice size (B images, 32 channels,
+48x32 latent positions), so that the host enqueue gap does not inflate the per-launch figure.
+    python tools/gc_one.py [B]        (ICM_GC_GENERIC=1 selects the strided-view kernel for comparison)"""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "image-compression-for-machine_b200"))
+import torch  # noqa: E402
+
+from compressai._native import NULL_VIEW, check, lib, stream_ptr, view_bcp  # noqa: E402
+from compressai.entropy_models import GaussianConditional  # noqa: E402
+from compressai.models.stf import get_scale_table  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+Z, P, M = 32, 48 * 32, 384
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(0)
+y = torch.randn(B * P, M, device=dev, generator=g) * 3
+mu = torch.randn(B * P, Z, device=dev, generator=g)
+sc = torch.rand(B * P, Z, device=dev, generator=g) * 5
+sup = torch.zeros(B * P, 608, device=dev, dtype=torch.bfloat16)
+y_hat = torch.zeros(B * P, M, device=dev)
+sym = torch.zeros(B, M * P, device=dev, dtype=torch.int32)
+idx = torch.zeros_like(sym)
+table = get_scale_table().float().to(dev)
+L = lib()
+st = stream_ptr()
+N = 200
+
+
+def run(name, fn, nbytes):
+    for _ in range(5):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(N):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / N * 1e3
+    print(f"{name:22s} {us:7.2f} us per launch   {nbytes / us / 1e6:6.2f} TB/s of {nbytes / 1e6:.1f} MB algorithmic traffic")
+
+
+n = B * Z * P
+i = 3
+run("gc_quantize_index", lambda: check(L.icm_gc_quantize_index(view_bcp(y, B, Z, P, Z * i), view_bcp(mu, B, Z, P), view_bcp(sc, B, Z, P), B, Z, P,
+                                                              table.data_ptr(), table.numel(), 0.11, sym.data_ptr(), idx.data_ptr(), M * P, Z * P * i,
+                                                              view_bcp(y_hat, B, Z, P, Z * i), view_bcp(sup, B, Z, P, M), NULL_VIEW, st)), n * 24)
+run("add_lrp", lambda: check(L.icm_add_lrp(view_bcp(y_hat, B, Z, P, Z * i), view_bcp(mu, B, Z, P), B, Z, P, view_bcp(sup, B, Z, P, M), NULL_VIEW, st)), n * 14)
