@@ -4,6 +4,7 @@
 // conv.cu on the tensor cores; these kernels keep its operands in channels-last bf16 so that no
 // permute/contiguous/roll/window_partition copy of the reference (stf.py:42-53,97,167-191) exists at all.
 #include "common.cuh"
+#include "mma_sync.cuh"
 
 namespace icm {
 
@@ -112,24 +113,6 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float *__restrict_
 // partition/reverse and the SW-MSA region mask are index arithmetic (stf.py:42-53,166-191,316-334).
 constexpr int WIN = 4, NTOK = 16, HD = 16;
 constexpr int ATT_WARPS = 8, ATT_JOBS_PER_WARP = 4; // per CTA: 32 (window, head) jobs share one copy of the bias table
-
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a)
-{
-    uint32_t d;
-    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
-    return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
-{
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t *>(&h2);
-}
 
 __global__ void __launch_bounds__(ATT_WARPS * 32) window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out,
                                                                const float *__restrict__ bias_table, int B, int H, int W, int C,

@@ -8,6 +8,9 @@
 //   - packing of ConvTranspose2d(k5, s2, p2, op1) weights into four 3x3 phase filters so that the transposed
 //     convolution runs on the same tcgen05 implicit-GEMM kernel with the PixelShuffle(2) store.
 #include "common.cuh"
+#include "mma_sync.cuh"
+
+#include <stdlib.h>
 
 namespace icm {
 
@@ -240,17 +243,159 @@ extern "C" int icm_eltwise_bf16(int mode, const void *d_a, int64_t pitch_a, cons
     return ICM_OK;
 }
 
+// Tensor-core version (mma.sync m16n8k16): one warp per (window, head).  K and V fragments of the whole window are
+// loaded once, straight from the channels-last qkv rows; the query rows are walked 16 at a time: S = Q K^T (head_dim
+// padded to a multiple of 16 with zero fragments), bias + shift mask + softmax on the accumulator fragment, which then
+// serves as the A operand of O = P V (V transposed in registers with movmatrix).  The scalar kernel above spends
+// 2 * N * HD FMAs and as many shared-memory loads per query row (12 ms per 64 images of 768x512 in WACNN).
+template <int WIN, int HD>
+__global__ void __launch_bounds__(128) win_attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out,
+                                                                const float *__restrict__ bias_table, int B, int H, int W, int C,
+                                                                int heads, int shift)
+{
+    constexpr int NT = WIN * WIN;        // tokens per window
+    constexpr int MT = NT / 16;          // 16-row query tiles
+    constexpr int NKT = NT / 8;          // 8-key tiles
+    constexpr int KS = (HD + 15) / 16;   // K = 16 steps of Q K^T
+    constexpr int DT = HD / 8;           // 8-column tiles of the output
+    constexpr int PK = NT / 16;          // K = 16 steps of P V
+    constexpr int NB = (2 * WIN - 1) * (2 * WIN - 1);
+    static_assert(NT % 16 == 0 && HD % 8 == 0, "window / head_dim not tileable");
+    extern __shared__ float s_bias[]; // [NB][heads]
+    for (int i = threadIdx.x; i < NB * heads; i += blockDim.x) s_bias[i] = bias_table[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int g = lane >> 2, t = lane & 3;
+    const int nWw = W / WIN, nWh = H / WIN;
+    const long long jobs = (long long)B * nWh * nWw * heads;
+    const float scale = rsqrtf((float)HD);
+    for (int rep = 0; rep < 2; ++rep) { // two (window, head) jobs per warp share one copy of the bias table
+    const long long job = ((long long)blockIdx.x * 4 + warp) * 2 + rep;
+    if (job >= jobs) break; // warp-uniform
+    const int head = (int)(job % heads);
+    long long tt = job / heads;
+    const int ww = (int)(tt % nWw); tt /= nWw;
+    const int wh = (int)(tt % nWh);
+    const int b = (int)(tt / nWh);
+    auto token_of = [&](int tok) -> long long { // window token -> position in the (unshifted) feature map
+        int h = wh * WIN + tok / WIN + shift, w = ww * WIN + tok % WIN + shift;
+        if (h >= H) h -= H;
+        if (w >= W) w -= W;
+        return ((long long)b * H + h) * W + w;
+    };
+    auto label_of = [&](int tok) -> int {
+        const int hs = wh * WIN + tok / WIN, ws = ww * WIN + tok % WIN;
+        return 3 * (hs < H - WIN ? 0 : (hs < H - shift ? 1 : 2)) + (ws < W - WIN ? 0 : (ws < W - shift ? 1 : 2));
+    };
+    // K as the B operand of S (k = channel pair, n = key), V in its natural fragment layout, then transposed
+    uint32_t kf[NKT][KS][2], vf[NKT][DT];
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(qkv + token_of(nt * 8 + g) * 3 * C + head * HD);
+        const uint32_t *rk = row + C / 2, *rv = row + C;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            kf[nt][ks][0] = (ks * 16 < HD) ? __ldg(rk + ks * 8 + t) : 0u;          // channels ks*16 + 2t, +1
+            kf[nt][ks][1] = (ks * 16 + 8 < HD) ? __ldg(rk + ks * 8 + 4 + t) : 0u;  // channels ks*16 + 8 + 2t, +1
+        }
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) vf[nt][dt] = __ldg(rv + dt * 4 + t);       // V[key][dt*8 + 2t, +1]
+    }
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) vf[nt][dt] = movmatrix_trans(vf[nt][dt]);  // -> (V[2t][dt*8+g], V[2t+1][dt*8+g]) of key tile nt
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+        const int tokA = mt * 16 + g, tokB = tokA + 8;
+        const long long tA = token_of(tokA), tB = token_of(tokB);
+        const uint32_t *qA = reinterpret_cast<const uint32_t *>(qkv + tA * 3 * C + head * HD);
+        const uint32_t *qB = reinterpret_cast<const uint32_t *>(qkv + tB * 3 * C + head * HD);
+        float sacc[NKT][4];
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t qa[4];
+            qa[0] = (ks * 16 < HD) ? __ldg(qA + ks * 8 + t) : 0u;
+            qa[1] = (ks * 16 < HD) ? __ldg(qB + ks * 8 + t) : 0u;
+            qa[2] = (ks * 16 + 8 < HD) ? __ldg(qA + ks * 8 + 4 + t) : 0u;
+            qa[3] = (ks * 16 + 8 < HD) ? __ldg(qB + ks * 8 + 4 + t) : 0u;
+#pragma unroll
+            for (int nt = 0; nt < NKT; ++nt) mma_bf16_16816(sacc[nt], qa, kf[nt][ks][0], kf[nt][ks][1]);
+        }
+        // bias + mask + softmax over the NT keys of rows tokA (slots 0, 1) and tokB (slots 2, 3)
+        const int labA = shift > 0 ? label_of(tokA) : 0, labB = shift > 0 ? label_of(tokB) : 0;
+        float mxA = -1e30f, mxB = -1e30f;
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int j = nt * 8 + 2 * t + c, jh = j / WIN, jw = j % WIN;
+                const float bA = s_bias[((tokA / WIN - jh + WIN - 1) * (2 * WIN - 1) + (tokA % WIN - jw + WIN - 1)) * heads + head];
+                const float bB = s_bias[((tokB / WIN - jh + WIN - 1) * (2 * WIN - 1) + (tokB % WIN - jw + WIN - 1)) * heads + head];
+                float vA = sacc[nt][c] * scale + bA, vB = sacc[nt][2 + c] * scale + bB;
+                if (shift > 0) {
+                    const int lj = label_of(j);
+                    if (lj != labA) vA += -100.0f;
+                    if (lj != labB) vB += -100.0f;
+                }
+                sacc[nt][c] = vA; sacc[nt][2 + c] = vB;
+                mxA = fmaxf(mxA, vA); mxB = fmaxf(mxB, vB);
+            }
+        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1)); mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
+        mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1)); mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
+        float dA = 0.f, dB = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                sacc[nt][c] = __expf(sacc[nt][c] - mxA); dA += sacc[nt][c];
+                sacc[nt][2 + c] = __expf(sacc[nt][2 + c] - mxB); dB += sacc[nt][2 + c];
+            }
+        dA += __shfl_xor_sync(0xffffffffu, dA, 1); dA += __shfl_xor_sync(0xffffffffu, dA, 2);
+        dB += __shfl_xor_sync(0xffffffffu, dB, 1); dB += __shfl_xor_sync(0xffffffffu, dB, 2);
+        const float iA = 1.0f / dA, iB = 1.0f / dB;
+        // O = P V with the (unnormalised) probabilities as A fragments
+        float oacc[DT][4];
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) { oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < PK; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);         pa[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+            pa[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]); pa[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+            for (int dt = 0; dt < DT; ++dt) mma_bf16_16816(oacc[dt], pa, vf[2 * kk][dt], vf[2 * kk + 1][dt]);
+        }
+        uint32_t *oA = reinterpret_cast<uint32_t *>(out + tA * C + head * HD), *oB = reinterpret_cast<uint32_t *>(out + tB * C + head * HD);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+            oA[dt * 4 + t] = pack_bf16(oacc[dt][0] * iA, oacc[dt][1] * iA);
+            oB[dt * 4 + t] = pack_bf16(oacc[dt][2] * iB, oacc[dt][3] * iB);
+        }
+    }
+    }
+}
+
 template <int WIN, int HD>
 static int launch_win_attention(const void *qkv, void *out, const float *bias, int B, int H, int W, int C, int heads, int shift, void *stream)
 {
     constexpr int N = WIN * WIN, NB = (2 * WIN - 1) * (2 * WIN - 1);
+    const long long jobs = (long long)B * (H / WIN) * (W / WIN) * heads;
+    static const bool scalar = getenv("ICM_WACNN_SCALAR_ATTENTION") != nullptr; // the CUDA-core kernel, kept for comparison
+    if (!scalar && NB * heads * sizeof(float) <= 48 * 1024) {
+        win_attention_mma_kernel<WIN, HD><<<(unsigned)((jobs + 7) / 8), 128, (size_t)NB * heads * sizeof(float), as_stream(stream)>>>(
+            (const __nv_bfloat16 *)qkv, (__nv_bfloat16 *)out, bias, B, H, W, C, heads, shift);
+        ICM_LAUNCH_CHECK();
+        return ICM_OK;
+    }
     const size_t smem = ((size_t)NB * heads + (size_t)4 * 2 * N * (HD + 1)) * sizeof(float);
     static thread_local bool configured = false;
     if (!configured && smem > 48 * 1024) {
         ICM_CUDA(cudaFuncSetAttribute(win_attention_kernel<WIN, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const long long jobs = (long long)B * (H / WIN) * (W / WIN) * heads;
     win_attention_kernel<WIN, HD><<<(unsigned)((jobs + 3) / 4), 128, smem, as_stream(stream)>>>(
         (const __nv_bfloat16 *)qkv, (__nv_bfloat16 *)out, bias, B, H, W, C, heads, shift);
     ICM_LAUNCH_CHECK();
