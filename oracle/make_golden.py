@@ -2,6 +2,7 @@
 
     python -m oracle.make_golden          # from the repo root; needs /root/reference
     python -m oracle.make_golden cnn      # only tests/golden/cnn_small.npz (WACNN, 256x256 = BASELINE configs[0])
+    python -m oracle.make_golden cnn2_full  # only tests/golden/cnn2_full.json (832x1216 = BASELINE configs[3], digests)
 
 Sources of truth used here:
   * the reference's shipped native binaries, executed through oracle/refbin.py (rANS, pmf->cdf);
@@ -257,9 +258,34 @@ def cnn_golden():
     print("cnn_small.npz", os.path.getsize(os.path.join(GOLD, "cnn_small.npz")))
 
 
+def cnn2_full_golden():
+    """BASELINE.json configs[3] size: the WACNN2 codec (identical layers to WACNN) on a 800x1216 image zero-padded to
+    832x1216, compressed by the reference on the CPU.  Only digests are stored (the y-string is 1.4 MB)."""
+    import torch.nn.functional as F
+
+    h = refshim.install("binary")
+    torch.manual_seed(0)
+    m = h["cnn"].WACNN().eval()
+    sd = weights.seeded_state_dict(m.state_dict(), seed=0, stress=True)
+    m.load_state_dict(sd)
+    m.update(force=True)
+    x = F.pad(weights.seeded_image((1, 3, 800, 1216), seed=5), (0, 0, 16, 16))
+    with torch.no_grad():
+        c = m.compress(x)
+    out = {"image": "seeded_image((1,3,800,1216), seed=5) padded (0,0,16,16)", "shape": list(c["shape"]),
+           "y_bytes": len(c["strings"][0][0]), "z_bytes": len(c["strings"][1][0]),
+           "y_sha1": sha1(c["strings"][0][0]), "z_sha1": sha1(c["strings"][1][0])}
+    with open(os.path.join(GOLD, "cnn2_full.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("cnn2_full:", out)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["cnn"]:
         cnn_golden()
+    elif sys.argv[1:] == ["cnn2_full"]:
+        cnn2_full_golden()
     else:
         main()
         cnn_golden()
+        cnn2_full_golden()

@@ -259,7 +259,7 @@ def test_input_validation(model):
         model.compress(torch.zeros(1, 3, 100, 128, device="cuda"))
 
 
-def test_config4_wacnn2_codec_at_832x1216(sd):
+def test_config4_wacnn2_codec_at_832x1216(sd, golden_dir):
     """BASELINE.json configs[3] as SURVEY.md §8d reads it: the WACNN2 codec on a 800x1216 image zero-padded to
     832x1216 (y 320x52x76 = 1 264 640 symbols, z 192x13x19).  Too large for the CPU oracle inside a test, so the
     size-independent properties are checked: decompress(compress(x)) == clamp(forward(x).x_hat) exactly, the strings of
@@ -282,6 +282,14 @@ def test_config4_wacnn2_codec_at_832x1216(sd):
     f = m(xp)
     assert f["likelihoods"]["y"].shape == (1, 320, 52, 76) and f["likelihoods"]["z"].shape == (1, 192, 13, 19)
     assert torch.equal(d["x_hat"], f["x_hat"].clamp(0, 1))
+    # stream sizes against the reference's own run of this image (digests in tests/golden/cnn2_full.json; the transforms run
+    # with bf16 operands here, so the bytes differ and only the sizes are comparable)
+    import json
+
+    gold = json.load(open(os.path.join(golden_dir, "cnn2_full.json")))
+    ny, nz = len(c["strings"][0][0]), len(c["strings"][1][0])
+    assert abs(ny - gold["y_bytes"]) / gold["y_bytes"] < 3e-2, (ny, gold["y_bytes"])
+    assert abs(nz - gold["z_bytes"]) / gold["z_bytes"] < 5e-2, (nz, gold["z_bytes"])
     # the y-string is a valid reference-format stream of exactly 1 264 640 symbols: decode it on the CPU with the
     # indexes of the GPU slice loop and re-encode
     y, h, w = m._analysis(xp)

@@ -184,3 +184,19 @@ def test_wacnn_restatement_matches_reference_model(golden_dir):
     assert c["strings"][0][0] == g["y_string"].tobytes()
     d = cnn_ref.decompress(sd, c["strings"], c["shape"], eb_tab=eb_tab)
     assert torch.allclose(d["x_hat"], torch.from_numpy(g["x_hat"]).clamp(0, 1), rtol=1e-3, atol=1e-4)
+
+
+def test_wacnn_restatement_at_config4_size(golden_dir):
+    """The 832x1216 WACNN2-codec case (BASELINE.json configs[3]): oracle/cnn_ref.py reproduces the reference's 1.4 MB
+    y-string and its z-string bit for bit (digests recorded from the reference by make_golden.py cnn2_full)."""
+    import hashlib
+    import json
+
+    g = json.load(open(os.path.join(golden_dir, "cnn2_full.json")))
+    sd = weights.seeded_state_dict(cnn_ref.template_state_dict(), seed=0, stress=True)
+    x = F.pad(weights.seeded_image((1, 3, 800, 1216), seed=5), (0, 0, 16, 16))
+    c = cnn_ref.compress(sd, x)
+    assert list(c["shape"]) == g["shape"] == [13, 19]
+    assert len(c["strings"][0][0]) == g["y_bytes"] and len(c["strings"][1][0]) == g["z_bytes"]
+    assert hashlib.sha1(c["strings"][0][0]).hexdigest() == g["y_sha1"]
+    assert hashlib.sha1(c["strings"][1][0]).hexdigest() == g["z_sha1"]
