@@ -2,6 +2,7 @@
 
     python -m oracle.make_golden          # from the repo root; needs /root/reference
     python -m oracle.make_golden cnn      # only tests/golden/cnn_small.npz (WACNN, 256x256 = BASELINE configs[0])
+    python -m oracle.make_golden stf_full   # only tests/golden/stf_full.json (768x512 = BASELINE configs[1], digests)
     python -m oracle.make_golden cnn2_full  # only tests/golden/cnn2_full.json (832x1216 = BASELINE configs[3], digests)
 
 Sources of truth used here:
@@ -280,8 +281,29 @@ def cnn2_full_golden():
     print("cnn2_full:", out)
 
 
+def stf_full_golden():
+    """BASELINE.json configs[1] size: STF on one 3x768x512 image, compressed by the reference on the CPU (digests only)."""
+    h = refshim.install("binary")
+    torch.manual_seed(0)
+    m = h["stf"].SymmetricalTransFormer().eval()
+    sd = weights.seeded_state_dict(m.state_dict(), seed=0, stress=True)
+    m.load_state_dict(sd)
+    m.update(force=True)
+    x = weights.seeded_image((1, 3, 768, 512), seed=9)
+    with torch.no_grad():
+        c = m.compress(x)
+    out = {"image": "seeded_image((1,3,768,512), seed=9)", "shape": list(c["shape"]),
+           "y_bytes": len(c["strings"][0][0]), "z_bytes": len(c["strings"][1][0]),
+           "y_sha1": sha1(c["strings"][0][0]), "z_sha1": sha1(c["strings"][1][0])}
+    with open(os.path.join(GOLD, "stf_full.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("stf_full:", out)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["cnn"]:
+    if sys.argv[1:] == ["stf_full"]:
+        stf_full_golden()
+    elif sys.argv[1:] == ["cnn"]:
         cnn_golden()
     elif sys.argv[1:] == ["cnn2_full"]:
         cnn2_full_golden()
@@ -289,3 +311,4 @@ if __name__ == "__main__":
         main()
         cnn_golden()
         cnn2_full_golden()
+        stf_full_golden()

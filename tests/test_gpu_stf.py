@@ -207,3 +207,21 @@ def test_stream_pipeline_equals_plain_api(model, chains, lag):
         assert torch.equal(x_hats[k], d["x_hat"])
         assert torch.equal(outs[k], d["x_hat"].cpu())
         assert strings[k][0] == c["strings"][0] and strings[k][1] == c["strings"][1]
+
+
+def test_full_size_stream_sizes_track_the_reference(model, golden_dir):
+    """The 768x512 image whose reference strings are recorded in tests/golden/stf_full.json: same latent shape, stream sizes
+    within a few percent (bf16 transforms), decompress(compress(x)) == clamp(forward(x))."""
+    import json
+
+    from oracle import weights
+
+    g = json.load(open(os.path.join(golden_dir, "stf_full.json")))
+    x = weights.seeded_image((1, 3, 768, 512), seed=9).cuda()
+    c = model.compress(x)
+    assert list(c["shape"]) == g["shape"]
+    ny, nz = len(c["strings"][0][0]), len(c["strings"][1][0])
+    assert abs(ny - g["y_bytes"]) / g["y_bytes"] < 3e-2, (ny, g["y_bytes"])
+    assert abs(nz - g["z_bytes"]) / g["z_bytes"] < 5e-2, (nz, g["z_bytes"])
+    d = model.decompress(c["strings"], c["shape"])
+    assert torch.equal(d["x_hat"], model(x)["x_hat"].clamp(0, 1))

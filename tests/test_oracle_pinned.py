@@ -200,3 +200,18 @@ def test_wacnn_restatement_at_config4_size(golden_dir):
     assert len(c["strings"][0][0]) == g["y_bytes"] and len(c["strings"][1][0]) == g["z_bytes"]
     assert hashlib.sha1(c["strings"][0][0]).hexdigest() == g["y_sha1"]
     assert hashlib.sha1(c["strings"][1][0]).hexdigest() == g["z_sha1"]
+
+
+def test_stf_restatement_at_config2_size(golden_dir):
+    """One 3x768x512 image (BASELINE.json configs[1]): oracle/stf_ref.py reproduces the reference's y- and z-strings bit
+    for bit (digests recorded from the reference by make_golden.py stf_full)."""
+    import hashlib
+    import json
+
+    g = json.load(open(os.path.join(golden_dir, "stf_full.json")))
+    sd = weights.seeded_state_dict(stf_ref.template_state_dict(), seed=0, stress=True)
+    c = stf_ref.compress(sd, weights.seeded_image((1, 3, 768, 512), seed=9))
+    assert list(c["shape"]) == g["shape"] == [12, 8]
+    assert len(c["strings"][0][0]) == g["y_bytes"] and len(c["strings"][1][0]) == g["z_bytes"]
+    assert hashlib.sha1(c["strings"][0][0]).hexdigest() == g["y_sha1"]
+    assert hashlib.sha1(c["strings"][1][0]).hexdigest() == g["z_sha1"]
