@@ -45,7 +45,7 @@ class Profile:
 
     _HOST = {"icm_last_error", "icm_abi_version", "icm_launch_count", "icm_pmf_to_quantized_cdf", "icm_tables_create",
              "icm_tables_destroy", "icm_rans_encode_workspace_bytes", "icm_rans_decoder_create", "icm_rans_decoder_destroy",
-             "icm_rans_decoder_set_streams", "icm_rans_decoder_status", "icm_set_conv_sm_limit", "icm_set_decoder_streams_per_cta"}
+             "icm_rans_decoder_set_streams", "icm_rans_decoder_status", "icm_set_conv_sm_limit", "icm_set_decoder_streams_per_cta", "icm_set_decoder_layout"}
 
     def __init__(self):
         self.records = {}
@@ -136,6 +136,7 @@ def _load():
         "icm_rans_decoder_set_streams": (I, [P, P, P, P, P]),
         "icm_rans_decoder_set_streams_device": (I, [P, P, P, P]),
         "icm_set_decoder_streams_per_cta": (I, [I]),
+        "icm_set_decoder_layout": (I, [I, I]),
         "icm_rans_decoder_step": (I, [P, P, P, I64, P, P]),
         "icm_rans_decoder_status": (I, [P, P, P]),
         "icm_gc_quantize_index": (I, [View, View, View, I, I, I64, P, I, F, P, P, I64, I64, View, View, View, P]),

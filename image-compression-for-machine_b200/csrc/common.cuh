@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <stdio.h>
 
 #include "icm_b200.h"
@@ -48,7 +49,17 @@ struct View {
 };
 static inline View as_view(const icm_view &v) { return View{(char *)v.ptr, v.sb, v.sc, v.sp}; }
 
-int sm_count();
+int sm_count();   // of the current device (cached per device)
+int current_device_ordinal();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (and per-kernel) setting, not a per-thread one: each
+// call site keeps the largest size it has configured on every device ordinal.
+constexpr int kMaxDeviceOrdinals = 64;
+struct PerDeviceSmem {
+    size_t configured[kMaxDeviceOrdinals] = {};
+    bool needs(size_t bytes) const { return bytes > configured[current_device_ordinal()]; }
+    void done(size_t bytes) { configured[current_device_ordinal()] = bytes; }
+};
 int persistent_grid_limit();          // SMs the persistent GEMM kernels may occupy (icm_set_conv_sm_limit)
 void set_persistent_grid_limit(int n);
 

@@ -478,10 +478,10 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     const size_t bias_bytes = (size_t)p.n_tiles * p.BN * 4;
     ICM_CHECK_ARG(bias_bytes <= 16 * 1024, "icm_conv2d: Cout=%d too wide for the bias staging area", a->Cout);
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4) * 8 + 16 + bias_bytes;
-    static thread_local size_t configured = 0;
-    if (smem_bytes > configured) {
+    static PerDeviceSmem configured;
+    if (configured.needs(smem_bytes)) {
         ICM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
+        configured.done(227 * 1024);
     }
     ICM_CHECK_ARG(m_tiles * p.n_tiles < (1 << 24) && p.tiles_w < 65536 && p.tiles_h < 65536, "icm_conv2d: too many tiles");
     p.total_tiles = (int)(m_tiles * p.n_tiles);

@@ -24,18 +24,21 @@ void set_error(const char *fmt, ...)
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int current_device_ordinal()
+{
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDeviceOrdinals ? dev : 0;
+}
+
 int sm_count()
 {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static int cached[kMaxDeviceOrdinals] = {};
+    const int dev = current_device_ordinal();
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return cached;
+    return cached[dev];
 }
 
 static thread_local int g_persistent_sm_limit = 0;

@@ -370,10 +370,10 @@ extern "C" int icm_swin_mlp(const void *d_h_bf16, const void *d_w1_packed, const
     p.bias_in_smem = smem_bytes + (size_t)5 * C * 4 <= budget;
     if (p.bias_in_smem) smem_bytes += (size_t)5 * C * 4;
     ICM_CHECK_ARG(smem_bytes <= 227 * 1024, "icm_swin_mlp: shared memory budget exceeded (%zu bytes)", smem_bytes);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static PerDeviceSmem configured;
+    if (configured.needs(smem_bytes)) {
         ICM_CUDA(cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        configured.done(227 * 1024);
     }
     const int max_ctas = persistent_grid_limit();
     const int grid = p.tiles < max_ctas ? p.tiles : max_ctas;

@@ -1,10 +1,12 @@
 // rANS coder on the GPU: the reference's 64-bit-state, 32-bit-renormalising coder, one state per
 // stream, bit-exact with compressai.ans (R1-R4 of SURVEY.md §8a; ryg rans64.h:59-142).
 //
-// A stream is a strictly serial recurrence, so its speed is (instructions per symbol) x (issue latency of a
-// lone warp, ~3.6 cycles measured on B200).  Both coders are therefore written to keep the per-symbol
-// instruction count minimal and branch-free on the common path; everything that does not depend on the
-// coder state is precomputed in parallel or fetched ahead of its use.
+// A stream is a strictly serial recurrence carried by ONE WARP, and a lone warp on B200 pays ~3-5 cycles per
+// instruction it issues (ncu, round 2: 5.1 cycles per issued instruction, of which 1.5 fixed-latency dependency
+// waits, 0.8 global-memory scoreboard, 0.6 branch resolution, 0.4 instruction fetch), so a stream's speed is set by
+// the NUMBER of instructions on the serial path.  Both coders therefore keep the per-symbol path short and straight,
+// and move everything that does not depend on the coder state into parallel kernels or into bulk work of the other
+// 31 lanes.
 //
 // Encoder = three kernels
 //   (1) rans_records_kernel   embarrassingly parallel: symbol -> 32-byte record {reciprocal of freq, renorm
@@ -16,13 +18,15 @@
 //                             symbol from a double-buffered shared-memory stage, one predicated store per
 //                             emitted word into a shared buffer that is drained coalesced between chunks.
 //   (3) rans_pack_kernel      moves every stream's bytes to its final offset in one packed buffer.
-// Decoder = one kernel, one warp per stream.  CDF rows (32-bit entries, each row followed by 31 sentinels
-//   so that any 32-entry window is safe), a per-table 2^k-entry "cum >> (16-k) -> first candidate" table
-//   and per-table metadata live in shared memory.  The table of symbol k+1 is known in advance (indexes
-//   are an input), so a speculative window of its row (the whole row for tables with <= 32 entries, else
-//   the 32 entries around the mode) is loaded while symbol k is decoded; every lane forms
-//   freq * (x >> 16) + cum - start for its own entry and the winner's result is shuffled out.
+// Decoder = one kernel per step, one warp per stream, state persists across steps (decode_stream is called 12 times
+//   per image):
+//   rans_decode_bucket_kernel per-table bucket tables in shared memory resolve a symbol from ONE LDS.128 and a few
+//                             compares / selects in registers (csrc/rans_lane.cuh); crowded buckets and escapes take
+//                             one out-of-line path.
+//   rans_decode_warp_kernel   round-1 kernel (speculative 32-entry window + ballot search), the fallback for table
+//                             sets that do not fit the bucket image or contain a symbol of frequency 65535.
 #include "common.cuh"
+#include "rans_lane.cuh"
 
 #include <new>
 #include <vector>
@@ -31,17 +35,20 @@ namespace icm {
 
 constexpr int kPrecision = 16;
 constexpr uint64_t kRansL = 1ull << 31;
-constexpr uint32_t kSentinel = 0x10000u; // == cdf[last]; also pads every row in the decoder's table
+constexpr uint32_t kSentinel = 0x10000u; // == cdf[last]; also pads every row in the fallback decoder's table
 constexpr int kRowPad = 31;
 
 struct TablesDev {
     int n_cdf, stride, lut_bits, total_pad;
-    const int32_t *cdf32;    // [n_cdf][stride]               (encoder gathers)
+    const int32_t *cdf32;    // [n_cdf][stride]
     const int32_t *sizes;    // [n_cdf]
     const int32_t *offsets;  // [n_cdf]
-    const uint32_t *cdf_pad; // decoder rows: size entries + 31 sentinels each
+    const uint32_t *cdf_pad; // fallback decoder rows: size entries + 31 sentinels each
     const int32_t *base;     // [n_cdf] first entry of row t inside cdf_pad
     const uint16_t *lut;     // [n_cdf << lut_bits]
+    // bucket decoder
+    const uint4 *image;      // shared-memory image (rans_lane.cuh), nullptr if the tables do not fit
+    uint32_t image_bytes, meta_off, row_off, rs, M;
 };
 
 }  // namespace icm
@@ -49,7 +56,8 @@ struct TablesDev {
 struct icm_tables {
     icm::TablesDev dev;
     void *d_blob;
-    size_t smem_bytes;
+    size_t smem_bytes;      // fallback decoder
+    size_t image_smem_bytes; // bucket decoder: image + alignment slack (per-warp areas come on top), 0 = not available
     int device;
 };
 
@@ -61,6 +69,7 @@ struct icm_rans_decoder {
     int64_t *d_nwords;   // [n_streams]
     const uint32_t *d_words;
     int32_t *d_status;
+    int device;
 };
 
 namespace icm {
@@ -97,6 +106,7 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // (1) records.  Per symbol a 32-byte record drives the branch-free state update
@@ -318,8 +328,9 @@ __global__ void __launch_bounds__(256) rans_pack_kernel(const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// decoder
-struct DecState {
+// fallback decoder (tables that do not fit the lane image): one WARP per stream, CDF rows with 32-bit entries in shared
+// memory, speculative 32-entry window + ballot search.  Kept from round 1; see the lane kernel below for the fast path.
+struct WDecState {
     uint32_t xl, xh;      // rANS state
     uint32_t pos;         // next stream word
     uint32_t wcur, wnxt;  // lane l: words (pos & ~31) + l and + 32 + l
@@ -339,13 +350,13 @@ __device__ __forceinline__ uint32_t dec_load_block(const DecCtx &c, uint32_t blo
 }
 
 // called after pos was incremented
-__device__ __forceinline__ void dec_after_consume(DecState &d, const DecCtx &c)
+__device__ __forceinline__ void dec_after_consume(WDecState &d, const DecCtx &c)
 {
     if ((d.pos & 31u) == 0) { d.wcur = d.wnxt; d.wnxt = dec_load_block(c, (d.pos >> 5) + 1); }
     d.wv = __shfl_sync(0xffffffffu, d.wcur, (int)(d.pos & 31u));
 }
 
-__device__ __forceinline__ uint32_t dec_get4(DecState &d, const DecCtx &c)
+__device__ __forceinline__ uint32_t dec_get4(WDecState &d, const DecCtx &c)
 { // Rans64DecGetBits, n_bits = 4
     const uint32_t val = d.xl & 15u;
     d.xl = (d.xl >> 4) | (d.xh << 28);
@@ -364,12 +375,12 @@ struct SlowArgs {
 };
 
 struct SlowRet {
-    DecState d;
+    WDecState d;
     int value;
 };
 
 // by value in, by value out: keeps the caller's state in registers (a reference would pin it to local memory)
-__device__ __noinline__ SlowRet dec_slow(DecState d, DecCtx c, SlowArgs a, uint32_t nxl, uint32_t nxh)
+__device__ __noinline__ SlowRet dec_slow(WDecState d, DecCtx c, SlowArgs a, uint32_t nxl, uint32_t nxh)
 {
     uint32_t s0 = a.s0, p = a.p;
     if (p - 1u >= 31u) { // general search: per-table bucket table, then windows until one brackets cum
@@ -412,7 +423,7 @@ __device__ __noinline__ SlowRet dec_slow(DecState d, DecCtx c, SlowArgs a, uint3
 constexpr int kDecWarps = 16; // max streams per CTA: they share one copy of the tables in shared memory; each warp is
                               // latency-bound (one instruction every ~4 cycles), so four per scheduler still interleave
 
-__global__ void __launch_bounds__(kDecWarps * 32) rans_decode_kernel(TablesDev T, int n_streams, const uint32_t *__restrict__ words,
+__global__ void __launch_bounds__(kDecWarps * 32) rans_decode_warp_kernel(TablesDev T, int n_streams, const uint32_t *__restrict__ words,
                                                          const int64_t *__restrict__ word_off,
                                                          const int64_t *__restrict__ nwords_arr,
                                                          uint64_t *__restrict__ state, int64_t *__restrict__ pos_arr,
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) rans_decode_kernel(TablesDev T
     ctx.W = words + word_off[s];
     ctx.nwords = (uint32_t)min((long long)nwords_arr[s], 0xFFFFFFFFLL);
     ctx.lane = lane;
-    DecState d;
+    WDecState d;
     {
         const long long pos0 = pos_arr[s];
         if (pos0 < 0) { // set_stream: Rans64DecInit
@@ -558,11 +569,169 @@ __global__ void __launch_bounds__(kDecWarps * 32) rans_decode_kernel(TablesDev T
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bucket decoder: one warp per stream, up to kDecMaxWarps streams per CTA share one copy of the image
+constexpr int kDecMaxWarps = 16;
+
+// warp-cooperative: load 32-word blocks until at least kRefillBelow words are ahead of position p; returns `loaded`
+__device__ __forceinline__ uint32_t bucket_refill(const lane::DecConst &c, uint32_t p, uint32_t ld, int lane_id)
+{
+    const lane::Smem sm{};
+    __syncwarp();
+    while ((int)(ld - p) < lane::kRefillBelow) { lane::ring_load_block(sm, c, ld, lane_id); ld += 32; }
+    __syncwarp();
+    return ld;
+}
+
+// the out-of-line path of a symbol (crowded bucket / escape).  By value in, by value out: keeps the caller's state
+// in registers (a reference would pin it to local memory), and one copy keeps the unrolled serial loop compact.
+struct RareRet {
+    lane::WarpDec d;
+    uint32_t pos, loaded;
+    int value;
+};
+__device__ __noinline__ RareRet bucket_rare(lane::DecConst c, lane::WarpDec d, uint32_t pos, uint32_t loaded, uint32_t a, uint32_t base,
+                                            uint32_t maxv, uint32_t rowinfo, lane::u4 E, int lane_id)
+{
+    const lane::Smem sm{};
+    auto refill = [&](uint32_t p, uint32_t &ld) { ld = bucket_refill(c, p, ld, lane_id); };
+    RareRet r;
+    r.value = lane::dec_rare(sm, c, d, pos, loaded, refill, a, base, maxv, rowinfo, E);
+    r.d = d; r.pos = pos; r.loaded = loaded;
+    return r;
+}
+
+__global__ void __launch_bounds__(kDecMaxWarps * 32) rans_decode_bucket_kernel(
+    TablesDev T, int n_streams, const uint32_t *__restrict__ words, const int64_t *__restrict__ word_off,
+    const int64_t *__restrict__ nwords_arr, uint64_t *__restrict__ state, int64_t *__restrict__ pos_arr,
+    const int32_t *__restrict__ idx, long long n_per_stream, int32_t *__restrict__ out, int32_t *__restrict__ status)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t raw_addr = smem_addr(smem_raw);
+    const uint32_t base = (raw_addr + lane::kAlign - 1) & ~(lane::kAlign - 1);
+    {
+        uint4 *d = reinterpret_cast<uint4 *>(smem_raw + (base - raw_addr));
+        for (uint32_t i = threadIdx.x; i < T.image_bytes / 16; i += blockDim.x) d[i] = __ldg(T.image + i);
+    }
+    __syncthreads();
+    // warp index broadcast from lane 0: tells the compiler it is warp-uniform (no divergence guards in the loop)
+    const int lane_id = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int s = blockIdx.x * (int)(blockDim.x >> 5) + wid;
+    if (s >= n_streams) return;
+
+    const lane::Smem sm{};
+    lane::DecConst c;
+    c.rs = T.rs; c.M = T.M;
+    c.ring = base + ((T.image_bytes + 15u) & ~15u) + (uint32_t)wid * lane::kWarpBytes;
+    c.W = words + word_off[s];
+    c.nwords = (uint32_t)min((long long)nwords_arr[s], 0xFFFFFFFFLL);
+    const uint32_t stage = c.ring + lane::kRingBytes, outs = stage + lane::kStageBytes, meta_addr = base + T.meta_off,
+                   row_addr = base + T.row_off;
+    const int32_t *I = idx + (size_t)s * n_per_stream;
+    int32_t *O = out + (size_t)s * n_per_stream;
+    const long long n = n_per_stream, n_chunks = (n + 31) / 32;
+    const int n_cdf = T.n_cdf;
+    bool bad = false;
+
+    // per-symbol table records of chunk ch (parity ch & 1); slot 32 of the other parity = its first symbol
+    auto stage_chunk = [&](long long ch, int t) {
+        if ((unsigned)t >= (unsigned)n_cdf) { bad = true; t = 0; } // the reference has only a compiled-out assert here (UB)
+        lane::u4 r = sm.ld128(meta_addr + 16u * (uint32_t)t);
+        r.x += base;
+        const uint32_t par = (uint32_t)(ch & 1) * (33u * 16u);
+        sm.st128(stage + par + 16u * (uint32_t)lane_id, r);
+        if (lane_id == 0) sm.st128(stage + (33u * 16u - par) + 32u * 16u, r);
+    };
+    uint32_t pos, loaded;
+    auto refill = [&](uint32_t p, uint32_t &ld) { return bucket_refill(c, p, ld, lane_id); };
+    lane::WarpDec d;
+    {
+        const long long pos0 = pos_arr[s];
+        if (pos0 < 0) { // set_stream: Rans64DecInit
+            d.xl = c.nwords > 0 ? __ldg(c.W) : 0u;
+            d.xh = c.nwords > 1 ? __ldg(c.W + 1) : 0u;
+            pos = 2;
+        } else {
+            const uint64_t x = state[s];
+            d.xl = (uint32_t)x; d.xh = (uint32_t)(x >> 32);
+            pos = (uint32_t)pos0;
+        }
+    }
+    loaded = pos & ~31u;
+    int ireg = lane_id < n ? __ldg(I + lane_id) : 0;
+    stage_chunk(0, ireg);
+    ireg = 32 + lane_id < n ? __ldg(I + 32 + lane_id) : 0;
+    loaded = refill(pos, loaded);
+    sm.ld64(lane::ring_slot(c, pos), d.wv, d.awv);
+    d.wa1 = lane::ring_slot(c, pos + 1);
+    uint32_t wa1_base = d.wa1;
+    lane::u4 mcur = sm.ld128(stage);
+    uint32_t a = (__funnelshift_r(d.xl, d.xl, c.rs) & c.M) | mcur.x;
+
+    for (long long ch = 0; ch < n_chunks; ++ch) {
+        __syncwarp();
+        if (ch + 1 < n_chunks) { // stage the next chunk; its indexes were fetched one chunk ago
+            stage_chunk(ch + 1, ireg);
+            const long long j = (ch + 2) * 32 + lane_id;
+            ireg = j < n ? __ldg(I + j) : 0;
+        }
+        pos += (d.wa1 - wa1_base) >> 3;
+        if ((int)(loaded - pos) < lane::kRefillBelow) loaded = refill(pos, loaded);
+        d.wa1 = lane::ring_slot(c, pos + 1);
+        wa1_base = d.wa1;
+        __syncwarp();
+        const int valid = (int)min(32LL, n - ch * 32);
+        const uint32_t sbase = stage + (uint32_t)(ch & 1) * (33u * 16u);
+        int k = 0;
+        while (k < valid) {
+            // straight run of common-path symbols; a symbol that needs the out-of-line path leaves the run, so the
+            // common path is fall-through code with one not-taken forward branch per symbol
+#pragma unroll 8
+            for (; k < valid; ++k) {
+                const lane::u4 mn = sm.ld128(sbase + 16u * (uint32_t)(k + 1)); // next symbol's table (slot 32 = next chunk's first)
+                const lane::u4 E = sm.ld128_ro(a);
+                int value;
+                if (!lane::dec_fast(sm, c, d, a, E, (int32_t)mcur.z, mn.x, value)) break;
+                sm.st32(outs + 4u * (uint32_t)k, (uint32_t)value);
+                mcur = mn;
+            }
+            if (k < valid) { // escape or crowded bucket
+                const lane::u4 mn = sm.ld128(sbase + 16u * (uint32_t)(k + 1));
+                pos += (d.wa1 - wa1_base) >> 3;
+                int value;
+                if (!lane::dec_escape_simple(sm, c, d, pos, loaded, mcur.y, mcur.w >> 16, value)) {
+                    const lane::u4 E = sm.ld128_ro(a);
+                    const RareRet r = bucket_rare(c, d, pos, loaded, a, base, mcur.y, row_addr + 8u * (mcur.w & 0xFFFFu), E, lane_id);
+                    d = r.d; pos = r.pos; loaded = r.loaded;
+                    value = r.value;
+                }
+                wa1_base = d.wa1;
+                a = (__funnelshift_r(d.xl, d.xl, c.rs) & c.M) | mn.x;
+                sm.st32(outs + 4u * (uint32_t)k, (uint32_t)(value + (int32_t)mcur.z));
+                mcur = mn;
+                ++k;
+            }
+        }
+        __syncwarp();
+        if (lane_id < valid) O[ch * 32 + lane_id] = (int32_t)sm.ld32(outs + 4u * (uint32_t)lane_id);
+    }
+    pos += (d.wa1 - wa1_base) >> 3;
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane_id == 0) {
+        state[s] = ((uint64_t)d.xh << 32) | d.xl;
+        pos_arr[s] = (int64_t)pos;
+        if (bad) status[s] = ICM_ERR_BAD_INDEX;
+    }
+}
+
 }  // namespace icm
 
 // =================================================================================================
 // C ABI
 using namespace icm;
+
+static int current_device() { return current_device_ordinal(); }
 
 extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, const int32_t *h_sizes,
                                  const int32_t *h_offsets, icm_tables **out)
@@ -581,16 +750,22 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
         base[t] = total;
         total += size + kRowPad;
     }
+    // bucket decoder image: what fits under the 227 KB of dynamic shared memory of one CTA beside 8 warps' work areas
+    const size_t image_budget = 226 * 1024 - lane::kAlign - 8 * lane::kWarpBytes;
+    lane::Image image = lane::build_image(h_cdfs, n_cdf, stride, h_sizes, h_offsets, image_budget);
+    // fallback decoder tables (rows with 32-bit entries + bucket table); its kernel also has 18 KB of static shared memory
     int lut_bits = 8;
     auto smem_need = [&](int bits) {
         return (size_t)((total + 3) & ~3) * 4 + ((size_t)n_cdf << bits) * 2 + (size_t)n_cdf * 16;
     };
-    while (lut_bits > 3 && smem_need(lut_bits) > 220 * 1024) --lut_bits;
-    ICM_CHECK_ARG(smem_need(lut_bits) <= 220 * 1024, "icm_tables_create: tables too large for shared memory");
-    const size_t lut_n = (size_t)n_cdf << lut_bits;
-    std::vector<uint32_t> cdf_pad(((size_t)total + 3) & ~(size_t)3, kSentinel);
+    const size_t legacy_budget = (227 - 19) * 1024;
+    while (lut_bits > 3 && smem_need(lut_bits) > legacy_budget) --lut_bits;
+    const bool legacy_ok = smem_need(lut_bits) <= legacy_budget;
+    ICM_CHECK_ARG(image.ok || legacy_ok, "icm_tables_create: tables too large for shared memory");
+    const size_t lut_n = legacy_ok ? (size_t)n_cdf << lut_bits : 0;
+    std::vector<uint32_t> cdf_pad(legacy_ok ? (((size_t)total + 3) & ~(size_t)3) : 0, kSentinel);
     std::vector<uint16_t> lut(lut_n);
-    for (int t = 0; t < n_cdf; ++t) {
+    for (int t = 0; legacy_ok && t < n_cdf; ++t) {
         const int size = h_sizes[t];
         const int32_t *c = h_cdfs + (size_t)t * stride;
         for (int j = 0; j < size; ++j) cdf_pad[base[t] + j] = (uint32_t)c[j];
@@ -601,18 +776,20 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
             lut[((size_t)t << lut_bits) + b] = (uint16_t)sidx;
         }
     }
-    // one device blob: cdf32 | sizes | offsets | base | cdf_pad | lut
+    // one device blob: cdf32 | sizes | offsets | base | cdf_pad | lut | image
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t img_bytes = image.ok ? image.bytes.size() : 0;
     const size_t o_cdf32 = 0, o_sizes = al(o_cdf32 + (size_t)n_cdf * stride * 4), o_offsets = al(o_sizes + n_cdf * 4),
                  o_base = al(o_offsets + n_cdf * 4), o_pad = al(o_base + n_cdf * 4),
-                 o_lut = al(o_pad + cdf_pad.size() * 4), blob_bytes = al(o_lut + lut_n * 2);
+                 o_lut = al(o_pad + cdf_pad.size() * 4), o_img = al(o_lut + lut_n * 2), blob_bytes = al(o_img + img_bytes + 16);
     std::vector<unsigned char> host(blob_bytes, 0);
     memcpy(&host[o_cdf32], h_cdfs, (size_t)n_cdf * stride * 4);
     memcpy(&host[o_sizes], h_sizes, n_cdf * 4);
     memcpy(&host[o_offsets], h_offsets, n_cdf * 4);
     memcpy(&host[o_base], base.data(), n_cdf * 4);
-    memcpy(&host[o_pad], cdf_pad.data(), cdf_pad.size() * 4);
-    memcpy(&host[o_lut], lut.data(), lut_n * 2);
+    if (!cdf_pad.empty()) memcpy(&host[o_pad], cdf_pad.data(), cdf_pad.size() * 4);
+    if (lut_n) memcpy(&host[o_lut], lut.data(), lut_n * 2);
+    if (img_bytes) memcpy(&host[o_img], image.bytes.data(), img_bytes);
     icm_tables *T = new (std::nothrow) icm_tables();
     ICM_CHECK_ARG(T, "icm_tables_create: out of host memory");
     if (cudaGetDevice(&T->device) != cudaSuccess) { delete T; set_error("icm_tables_create: no CUDA device"); return ICM_ERR_NO_DEVICE; }
@@ -622,8 +799,11 @@ extern "C" int icm_tables_create(const int32_t *h_cdfs, int n_cdf, int stride, c
     char *b = (char *)T->d_blob;
     T->dev = TablesDev{n_cdf, stride, lut_bits, total,
                        (const int32_t *)(b + o_cdf32), (const int32_t *)(b + o_sizes), (const int32_t *)(b + o_offsets),
-                       (const uint32_t *)(b + o_pad), (const int32_t *)(b + o_base), (const uint16_t *)(b + o_lut)};
-    T->smem_bytes = smem_need(lut_bits);
+                       legacy_ok ? (const uint32_t *)(b + o_pad) : nullptr, (const int32_t *)(b + o_base),
+                       legacy_ok ? (const uint16_t *)(b + o_lut) : nullptr,
+                       image.ok ? (const uint4 *)(b + o_img) : nullptr, (uint32_t)img_bytes, image.meta_off, image.row_off, image.rs, image.M};
+    T->smem_bytes = legacy_ok ? smem_need(lut_bits) : 0;
+    T->image_smem_bytes = image.ok ? ((img_bytes + 15) & ~(size_t)15) + lane::kAlign : 0;
     *out = T;
     return ICM_OK;
 }
@@ -671,6 +851,7 @@ extern "C" int icm_rans_encode_batch(const icm_tables *t, const int32_t *d_symbo
     ICM_CHECK_ARG(n_streams > 0 && n_per_stream >= 0, "icm_rans_encode_batch: bad sizes");
     ICM_CHECK_ARG(n_per_stream == 0 || (d_symbols && d_indexes), "icm_rans_encode_batch: null symbols");
     ICM_CHECK_ARG(((uintptr_t)d_packed & 3) == 0 && ((uintptr_t)d_work & 255) == 0, "icm_rans_encode_batch: misaligned buffers");
+    ICM_CHECK_ARG(t->device == current_device(), "icm_rans_encode_batch: tables were created on device %d", t->device);
     cudaStream_t st = as_stream(stream);
     const EncLayout L = enc_layout(n_streams, n_per_stream);
     char *w = (char *)d_work;
@@ -702,6 +883,7 @@ extern "C" int icm_rans_decoder_create(int n_streams, icm_rans_decoder **out)
     ICM_CHECK_ARG(d, "icm_rans_decoder_create: out of host memory");
     d->n_streams = n_streams;
     d->d_words = nullptr;
+    d->device = current_device();
     char *blob = nullptr;
     const size_t per = 8 + 8 + 8 + 8 + 4;
     cudaError_t e = cudaMalloc(&blob, per * n_streams + 64);
@@ -755,14 +937,29 @@ extern "C" int icm_rans_decoder_set_streams_device(icm_rans_decoder *d, const ui
     return ICM_OK;
 }
 
-// Streams per decoder CTA (1, 2, 4, 8 or 16; 0 = automatic).  One stream per CTA is fastest per stream (a whole SM to
-// itself); more streams per CTA share one copy of the tables in shared memory and leave more SMs to other
-// kernels -- what a pipeline that overlaps the decoder with the convolutions wants.
-static thread_local int g_dec_warps = 0;
-extern "C" int icm_set_decoder_streams_per_cta(int n)
+// Streams (warps) per decoder CTA: 0 = automatic, else a power of two <= 16.  One stream per CTA is fastest per stream
+// (a whole SM to itself); more streams per CTA share one copy of the tables in shared memory and leave more SMs to
+// other kernels -- what a pipeline that overlaps the decoder with the convolutions wants.  kernel: 0 = bucket kernel
+// when the tables fit, 1 = force the round-1 warp-search kernel (A/B tests).
+static thread_local int g_dec_warps = 0, g_dec_kernel = 0;
+extern "C" int icm_set_decoder_layout(int streams_per_cta, int kernel)
 {
-    ICM_CHECK_ARG(n == 0 || n == 1 || n == 2 || n == 4 || n == 8 || n == 16, "icm_set_decoder_streams_per_cta: %d is not 0, 1, 2, 4, 8 or 16", n);
-    g_dec_warps = n;
+    ICM_CHECK_ARG(streams_per_cta >= 0 && streams_per_cta <= 16 && (streams_per_cta & (streams_per_cta - 1)) == 0,
+                  "icm_set_decoder_layout: streams_per_cta %d is not 0, 1, 2, 4, 8 or 16", streams_per_cta);
+    ICM_CHECK_ARG(kernel == 0 || kernel == 1, "icm_set_decoder_layout: kernel %d is not 0 or 1", kernel);
+    g_dec_warps = streams_per_cta;
+    g_dec_kernel = kernel;
+    return ICM_OK;
+}
+extern "C" int icm_set_decoder_streams_per_cta(int n) { return icm_set_decoder_layout(n, g_dec_kernel); }
+
+template <class K>
+static int ensure_smem(K kernel, size_t bytes, PerDeviceSmem &configured)
+{
+    if (configured.needs(bytes)) {
+        ICM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured.done(bytes);
+    }
     return ICM_OK;
 }
 
@@ -771,17 +968,30 @@ extern "C" int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, c
 {
     ICM_CHECK_ARG(d && t && d->d_words, "icm_rans_decoder_step: decoder has no stream (call set_streams first)");
     ICM_CHECK_ARG(n_per_stream >= 0 && (n_per_stream == 0 || (d_indexes && d_out)), "icm_rans_decoder_step: bad arguments");
+    const int dev = current_device();
+    ICM_CHECK_ARG(t->device == dev && d->device == dev, "icm_rans_decoder_step: tables (device %d) / decoder (device %d) used on device %d",
+                  t->device, d->device, dev);
     if (n_per_stream == 0) return ICM_OK;
-    static thread_local size_t configured = 0;
-    if (t->smem_bytes > configured) {
-        ICM_CUDA(cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem_bytes));
-        configured = t->smem_bytes;
-    }
+    const int S = d->n_streams;
     int warps = g_dec_warps;
-    if (warps == 0) warps = d->n_streams <= sm_count() / 2 ? 1 : (d->n_streams <= sm_count() ? 2 : 4);
-    while (d->n_streams % warps) warps >>= 1; // full CTAs only
-    rans_decode_kernel<<<(d->n_streams + warps - 1) / warps, warps * 32, t->smem_bytes, as_stream(stream)>>>(
-        t->dev, d->n_streams, d->d_words, d->d_word_off, d->d_nwords, d->d_state, d->d_pos, d_indexes, n_per_stream, d_out, d->d_status);
+    if (warps == 0) warps = S <= sm_count() / 2 ? 1 : (S <= sm_count() ? 2 : 4);
+    if (t->image_smem_bytes && !(g_dec_kernel == 1 && t->smem_bytes)) {
+        const size_t room = (size_t)227 * 1024 - t->image_smem_bytes;
+        while (warps > 1 && (size_t)warps * lane::kWarpBytes > room) warps >>= 1;
+        const size_t smem = t->image_smem_bytes + (size_t)warps * lane::kWarpBytes;
+        static PerDeviceSmem conf_b;
+        if (int rc = ensure_smem(rans_decode_bucket_kernel, smem, conf_b)) return rc;
+        rans_decode_bucket_kernel<<<(S + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(
+            t->dev, S, d->d_words, d->d_word_off, d->d_nwords, d->d_state, d->d_pos, d_indexes, n_per_stream, d_out, d->d_status);
+        ICM_LAUNCH_CHECK();
+        return ICM_OK;
+    }
+    ICM_CHECK_ARG(t->smem_bytes, "icm_rans_decoder_step: these tables only fit the bucket decoder");
+    static PerDeviceSmem conf_w;
+    if (int rc = ensure_smem(rans_decode_warp_kernel, t->smem_bytes, conf_w)) return rc;
+    while (S % warps) warps >>= 1; // full CTAs only
+    rans_decode_warp_kernel<<<(S + warps - 1) / warps, warps * 32, t->smem_bytes, as_stream(stream)>>>(
+        t->dev, S, d->d_words, d->d_word_off, d->d_nwords, d->d_state, d->d_pos, d_indexes, n_per_stream, d_out, d->d_status);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }

@@ -502,10 +502,11 @@ extern "C" int icm_final_conv(const void *d_in_bf16, const float *d_w, const flo
     }
     const size_t smem = (size_t)(FT + 2) * (FT + 2) * (C / 2 + 1) * 4 + (size_t)27 * C * 4;
     dim3 grid((W + FT - 1) / FT, (H + FT - 1) / FT, B);
-    static thread_local bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        ICM_CUDA(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
+    static PerDeviceSmem configured;
+    if (smem > 48 * 1024 && configured.needs(smem)) {
+        ICM_CHECK_ARG(smem <= 227 * 1024, "icm_final_conv: C=%d needs %zu bytes of shared memory", C, smem);
+        ICM_CUDA(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.done(smem);
     }
     final_conv_kernel<<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16 *)d_in_bf16, d_w, d_b, d_img, B, H, W, C, clamp01);
     ICM_LAUNCH_CHECK();

@@ -391,10 +391,10 @@ static int launch_win_attention(const void *qkv, void *out, const float *bias, i
         return ICM_OK;
     }
     const size_t smem = ((size_t)NB * heads + (size_t)4 * 2 * N * (HD + 1)) * sizeof(float);
-    static thread_local bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    static PerDeviceSmem configured;
+    if (smem > 48 * 1024 && configured.needs(smem)) {
         ICM_CUDA(cudaFuncSetAttribute(win_attention_kernel<WIN, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.done(smem);
     }
     win_attention_kernel<WIN, HD><<<(unsigned)((jobs + 3) / 4), 128, smem, as_stream(stream)>>>(
         (const __nv_bfloat16 *)qkv, (__nv_bfloat16 *)out, bias, B, H, W, C, heads, shift);

@@ -83,8 +83,12 @@ int icm_rans_decoder_set_streams(icm_rans_decoder *d, const uint8_t *d_bytes, co
 /* Same, for streams that are already on the device as icm_rans_encode_batch left them: d_bytes = its
  * d_packed, d_sizes = its int32 byte sizes (streams back to back in order).  No host synchronisation. */
 int icm_rans_decoder_set_streams_device(icm_rans_decoder *d, const uint8_t *d_bytes, const int32_t *d_sizes, void *stream);
-/* Streams per decoder CTA: 1, 2, 4, 8 or 16 (0 = automatic: 1 up to 74 streams).  See csrc/rans.cu. */
-int icm_set_decoder_streams_per_cta(int n);
+/* Streams (= warps) per decoder CTA: 0 = automatic, else 1, 2, 4, 8 or 16.  They share one copy of the tables in
+ * shared memory: one stream per CTA is fastest per stream, many streams per CTA leave the other SMs to the
+ * convolutions.  kernel = 1 forces the round-1 warp-search kernel (the fallback for table sets that do not fit the
+ * bucket image; A/B tests).  Thread-local.  See csrc/rans.cu. */
+int icm_set_decoder_layout(int streams_per_cta, int kernel);
+int icm_set_decoder_streams_per_cta(int n); /* = icm_set_decoder_layout(n, current kernel) */
 /* Decodes the next n_per_stream symbols of every stream.  d_indexes / d_out: [n_streams][n_per_stream]. */
 int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, const int32_t *d_indexes,
                           int64_t n_per_stream, int32_t *d_out, void *stream);
