@@ -6,7 +6,9 @@
         bench.py --gpus N --steps K --warmup W
 
 One "step" = compress + decompress of one batch of B synthetic 3x768x512 images per GPU (BASELINE.json
-configs[2] on each GPU; the batch shards across GPUs with no collective, weak scaling).  Prints ONE JSON line:
+configs[2] on each GPU; the batch shards across GPUs with no collective).  --scaling weak (default): B images per
+GPU whatever N; --scaling strong: B images in total, B / N per GPU (configs[2] as written: 64 images sharded over
+1/2/4/8 GPUs).  Prints ONE JSON line:
 
   value         images/s, whole job, inputs and bit-streams resident in HBM (CUDA events, max over ranks)
   e2e           the same metric through the public API with HOST buffers: pinned-host image -> H2D ->
@@ -14,6 +16,9 @@ configs[2] on each GPU; the batch shards across GPUs with no collective, weak sc
   roofline      dominant kernel family of a step (per-call CUDA events in a separate instrumented step)
   cpu_baseline  the pinned CPU oracle (oracle/stf_ref.py + oracle/rans_oracle.c: the restatement of the
                 reference's path) on this box's host cores, on a bounded sample of the same workload
+  stress        the same pipeline with the survey's rate-raising weights (many CDF tables, ~26 % escapes): the
+                default-initialised weights are the coder's easiest case (every y index is 0)
+  latency_b1    BASELINE configs[1]: one 3x768x512 image, compress + decompress through the plain API, one at a time
   --impl reference   times only that CPU path (rank 0), same metric / config, and prints its own line.
 """
 import os as _os
@@ -139,6 +144,15 @@ def cpu_reference_step(sd, x, tabs):
     return c, d
 
 
+def reference_state_dict(weights="default"):
+    """STF parameters for the CPU arm without importing the repo's package (no native library is loaded by that arm):
+    the oracle's own template + seeded values scaled like PyTorch's default initialisers (oracle/weights.py)."""
+    from oracle import stf_ref
+    from oracle import weights as oracle_weights
+
+    return oracle_weights.seeded_state_dict(stf_ref.template_state_dict(), seed=0, stress=(weights == "stress"))
+
+
 def cpu_baseline(model_sd, n_images, steps=1, warmup=0):
     from oracle import entropy, stf_ref
 
@@ -169,12 +183,24 @@ def main():
     ap.add_argument("--dec-per-cta", type=int, default=8, help="rANS decoder streams per CTA in the pipeline (1, 2, 4, 8, 16)")
     ap.add_argument("--lag", type=int, default=8, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag")
     ap.add_argument("--chains", type=int, default=2, help="pipeline: jobs allowed in a throughput-bound phase at once (0 = unordered)")
-    ap.add_argument("--conv-sms", type=int, default=-1, help="cap on SMs used by the conv kernel (0 = all, -1 = automatic)")
+    ap.add_argument("--conv-sms", type=int, default=0, help="cap on SMs used by the conv kernel (0 = all: its tile scheduler is dynamic)")
+    ap.add_argument("--decode-priority", type=int, default=1, help="pipeline: run each job's decode loop on a high-priority stream")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch images per GPU; strong: --batch images in total")
+    ap.add_argument("--no-stress", action="store_true", help="skip the stress-weights sub-record")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency sub-record")
+    ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU arm / cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"stf 3x{H_IMG}x{W_IMG}, {args.batch} images per GPU per step (BASELINE.json configs[2]; batch sharded, no collective)"
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--scaling strong: --batch {args.batch} is not a multiple of the {world} GPUs")
+        total_images, args.batch = args.batch, args.batch // world
+        workload = (f"stf 3x{H_IMG}x{W_IMG}, {total_images} images per step in total = {args.batch} per GPU "
+                    f"(BASELINE.json configs[2] as written; batch sharded, no collective)")
+    else:
+        workload = f"stf 3x{H_IMG}x{W_IMG}, {args.batch} images per GPU per step (BASELINE.json configs[2] on every GPU; batch sharded, no collective)"
     config = {"workload": workload, "images_per_gpu": args.batch, "height": H_IMG, "width": W_IMG,
               "weights": WEIGHTS[args.weights], "l2": "inputs larger than L2 (302 MB per batch at B=64)",
               "pipeline": f"{args.streams} CUDA streams x jobs of {args.part} images (compress -> decompress per job), K steps in flight; "
@@ -185,15 +211,19 @@ def main():
             return 0
         # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core this process may run on
         torch.set_num_threads(len(os.sched_getaffinity(0)))
-        mm = make_model("cpu", args.weights)  # parameter container only; the timed path below is oracle/ on the CPU
-        ips, dt = cpu_baseline(mm.state_dict(), 2, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        n_cpu = max(1, args.cpu_images)
+        warm = max(1, min(args.warmup, 1))
+        ips, dt = cpu_baseline(reference_state_dict(args.weights), n_cpu, steps=max(1, args.steps), warmup=warm)
         cores = torch.get_num_threads()
+        sample = (f"{n_cpu} images (3x768x512) compress+decompress per timed step (a bounded sample of the {args.batch}-image workload; "
+                  f"images/s = {n_cpu} / step time), {warm} untimed warm-up step, oracle/stf_ref.py fp32 + oracle/rans_oracle.c; "
+                  f"parameters from oracle/weights.py (the repo's package and native library are not loaded by this arm)")
+        config["cpu_sample_images_per_step"] = n_cpu
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "2 images (3x768x512) compress+decompress per step, oracle/stf_ref.py fp32 + oracle/rans_oracle.c"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
@@ -220,13 +250,16 @@ def main():
 
     from compressai.utils.pipeline import RoundTripPipeline
 
-    pipe = RoundTripPipeline(model, n_streams=args.streams, part=min(args.part, B), conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
-                             decoder_streams_per_cta=args.dec_per_cta, lag=args.lag, chains=args.chains)
+    def make_pipe(mdl):
+        return RoundTripPipeline(mdl, n_streams=args.streams, part=min(args.part, B), conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
+                                 decoder_streams_per_cta=args.dec_per_cta, lag=args.lag, chains=args.chains, decode_priority=bool(args.decode_priority))
+
+    pipe = make_pipe(model)
     out_bufs = [out_host, torch.empty_like(out_host).pin_memory()] if not args.no_e2e else []
 
-    def run_device(steps):
+    def run_device(steps, p=None):
         """K steps = K batches through the stream pipeline, images and bit-streams resident in HBM."""
-        return pipe.roundtrip([x_dev] * steps, keep_outputs=False)  # a server hands x_hat on and releases it
+        return (p or pipe).roundtrip([x_dev] * steps, keep_outputs=False)  # a server hands x_hat on and releases it
 
     def run_e2e(steps):
         """K steps through the host-facing path: pinned images -> H2D -> compress -> streams to the host and back
@@ -268,6 +301,15 @@ def main():
     warm_steps = max(args.warmup, 3, -(-args.streams // jobs_per_step))
     run_device(warm_steps)
     torch.cuda.synchronize()
+    # the device-resident pipeline (no per-job host read) must give exactly what the host-string API gives
+    check_n = min(B, 2)
+    xh_dev, _ = pipe.roundtrip([x_dev[:check_n]], keep_outputs=True)
+    c_host = model.compress(x_dev[:check_n])
+    xh_host = model.decompress(c_host["strings"], c_host["shape"])["x_hat"]
+    torch.cuda.synchronize()
+    if not torch.equal(xh_dev[0], xh_host):
+        raise SystemExit("bench: the device-resident pipeline and the host-string API disagree on x_hat")
+    del xh_dev, xh_host, c_host
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -287,6 +329,37 @@ def main():
                "d2h_bytes_per_step": out_host.numel() * 4 + pipe_capacity_bytes(B), "ms_per_step": round(ms_e2e / args.steps, 3),
                "timing": "wall clock around K pipelined steps incl. creation of the Python byte strings"}
 
+    # the same pipeline with the survey's stress weights: many CDF tables in use, ~26 % escape symbols (the coder's hard case)
+    stress = None
+    if not args.no_stress and args.weights != "stress":
+        m2 = make_model(dev, "stress")
+        p2 = make_pipe(m2)
+        run_device(warm_steps, p2)
+        torch.cuda.synchronize()
+        ms2, _, _ = timed(lambda k: run_device(k, p2), args.steps)
+        c2 = m2.compress(x_dev[:min(B, 4)])
+        nb2 = sum(len(s_) for s_ in c2["strings"][0]) / min(B, 4)
+        stress = {"value": round(n_img / (ms2 / 1e3), 3), "unit": "images/s", "ms_per_step": round(ms2 / args.steps, 3),
+                  "weights": WEIGHTS["stress"], "y_bytes_per_image": round(nb2, 1), "timing": "as `value`: device-resident pipeline, CUDA events"}
+        del m2, p2, c2
+        torch.cuda.empty_cache()
+    # BASELINE configs[1]: one image at a time through the plain API (host strings), median of 7
+    latency = None
+    if rank == 0 and not args.no_latency:
+        x1 = x_dev[:1]
+        ts = []
+        for it in range(9):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c1 = model.compress(x1)
+            d1 = model.decompress(c1["strings"], c1["shape"])
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts = sorted(ts[2:])
+        latency = {"ms": round(ts[len(ts) // 2], 2), "images_per_s": round(1e3 / ts[len(ts) // 2], 2),
+                   "workload": "stf 1x3x768x512 compress + decompress (BASELINE.json configs[1]), plain API, host byte strings, one image at a time",
+                   "timing": "wall clock incl. host enqueue and synchronisation, median of 7 after 2 warm-up runs"}
+        del c1, d1
     # instrumented step: per-entry-point CUDA events -> dominant kernel family and its roofline
     roofline, families = None, None
     if rank == 0:
@@ -330,17 +403,20 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(len(os.sched_getaffinity(0)))
-        ips, dt = cpu_baseline(model.state_dict(), 2, steps=1, warmup=0)
+        n_cpu = max(1, args.cpu_images)
+        ips, dt = cpu_baseline(model.state_dict(), n_cpu, steps=2, warmup=1)
         cpu = {"value": round(ips, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"2 images (3x768x512) compress+decompress once ({dt:.1f} s), oracle/stf_ref.py fp32 + oracle/rans_oracle.c"}
+               "sample": f"{n_cpu} images (3x768x512) compress+decompress per step, 1 warm-up + 2 timed steps ({dt:.1f} s each), "
+                         f"same weights as the GPU arm, oracle/stf_ref.py fp32 + oracle/rans_oracle.c"}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm_steps,
-            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16 operands / fp32 accumulate (transforms); fp32 (entropy models); u64 (rANS)", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "families": families,
+            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "stress": stress, "latency_b1": latency,
+            "families": families,
             "msym_per_s": round(value * SYMBOLS_PER_IMAGE / 1e6, 2),
             "bytes_per_image": round(str_bytes / B, 1),
         }))

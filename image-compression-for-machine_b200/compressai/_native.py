@@ -139,6 +139,8 @@ def _load():
         "icm_set_decoder_layout": (I, [I, I]),
         "icm_rans_decoder_step": (I, [P, P, P, I64, P, P]),
         "icm_rans_decoder_status": (I, [P, P, P]),
+        "icm_rans_decoder_status_min": (I, [P, P, P]),
+        "icm_min_i32": (I, [P, I64, P, P]),
         "icm_gc_quantize_index": (I, [View, View, View, I, I, I64, P, I, F, P, P, I64, I64, View, View, View, P]),
         "icm_gc_build_indexes": (I, [View, I, I, I64, P, I, F, P, I64, I64, P]),
         "icm_gc_dequantize": (I, [P, I64, I64, View, I, I, I64, View, View, View, P]),

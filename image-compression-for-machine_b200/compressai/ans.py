@@ -90,20 +90,33 @@ _table_cache = {}
 
 
 def _tables_from_args(cdfs, cdfs_sizes, offsets):
+    """Device tables for the reference-style (cdfs, cdfs_sizes, offsets) arguments.  The reference converts the whole
+    list-of-lists on every call; here the lists are flattened once per call and the device copy is reused whenever
+    the CONTENT is unchanged (keyed on a digest, so lists mutated in place are never served stale tables)."""
     if isinstance(cdfs, Tables):
         return cdfs
-    # the reference re-converts the whole table on every call; we key on the list objects (kept alive by
-    # the cache entry) plus a cheap content probe
-    probe = (len(cdfs), tuple(cdfs[0][:4]), tuple(cdfs[-1][:4]), int(cdfs_sizes[-1]), int(offsets[-1])) if not isinstance(cdfs, torch.Tensor) else None
-    key = (id(cdfs), id(cdfs_sizes), id(offsets), probe)
+    import hashlib
+
+    to_np = lambda v: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)).astype(np.int32)
+    if isinstance(cdfs, (torch.Tensor, np.ndarray)):
+        rows = np.ascontiguousarray(to_np(cdfs))
+    else:
+        width = max(len(r) for r in cdfs)
+        rows = np.zeros((len(cdfs), width), np.int32)
+        for i, r in enumerate(cdfs):
+            rows[i, : len(r)] = r
+    sizes, offs = np.ascontiguousarray(to_np(cdfs_sizes).reshape(-1)), np.ascontiguousarray(to_np(offsets).reshape(-1))
+    h = hashlib.blake2b(digest_size=16)
+    for a in (np.asarray(rows.shape, np.int64), rows, sizes, offs):
+        h.update(a.tobytes())
+    key = (torch.cuda.current_device() if torch.cuda.is_available() else -1, h.digest())
     hit = _table_cache.get(key)
-    if hit is not None:
-        return hit[0]
-    t = Tables(cdfs, cdfs_sizes, offsets)
-    if len(_table_cache) > 16:
-        _table_cache.clear()
-    _table_cache[key] = (t, cdfs, cdfs_sizes, offsets)
-    return t
+    if hit is None:
+        hit = Tables(rows, sizes, offs)
+        if len(_table_cache) > 16:
+            _table_cache.clear()
+        _table_cache[key] = hit
+    return hit
 
 
 _workspaces = {}
@@ -118,10 +131,31 @@ def _workspace(nbytes, device):
     return w
 
 
-def encode_streams(tables, symbols, indexes, return_device=False):
+def raise_for_status(code, what="rANS coder"):
+    """Map a (folded) device status word to the exception the host-string path raises."""
+    if code == _ERR_BAD_INDEX:
+        raise ValueError(f"{what}: CDF index out of range")
+    if code == _ERR_CAPACITY:
+        raise CapacityError(f"{what}: bit-stream larger than the optimistic 16 bit/symbol buffer")
+    if code < 0:
+        raise NativeError(f"{what}: device status {code}")
+
+
+class CapacityError(NativeError):
+    """The asynchronous encoder's optimistic output buffer was too small; retry with worst_case=True."""
+
+
+def fold_status(values, flag):
+    """flag (CUDA int32[1]) = min(flag, values): asynchronous, no host synchronisation."""
+    check(lib().icm_min_i32(values.data_ptr(), values.numel(), flag.data_ptr(), stream_ptr()), "icm_min_i32")
+
+
+def encode_streams(tables, symbols, indexes, return_device=False, worst_case=False):
     """Encode S independent streams.  symbols / indexes: CUDA int32 [S, N] in stream order.
 
-    Returns a list of S `bytes` (or, with return_device=True, (packed uint8 CUDA tensor, sizes list))."""
+    Returns a list of S `bytes` (or, with return_device=True, (packed uint8 CUDA tensor, sizes list)).
+    return_device="async": (packed, sizes int32[S+1]) with no host synchronisation; a negative size is an ICM_ERR_* code
+    (the output buffer holds 16 bit/symbol unless worst_case=True: 7 bytes/symbol)."""
     assert symbols.is_cuda and indexes.is_cuda and symbols.dtype == torch.int32 and indexes.dtype == torch.int32
     S, N = symbols.shape
     assert indexes.shape == symbols.shape
@@ -130,7 +164,7 @@ def encode_streams(tables, symbols, indexes, return_device=False):
     L = lib()
     work = _workspace(L.icm_rans_encode_workspace_bytes(S, N), dev)
     sizes = torch.empty(S + 1, dtype=torch.int32, device=dev)
-    cap = S * (2 * N + 64)  # 16 bit/symbol: ample for model data; retried at the worst case if exceeded
+    cap = S * (7 * N + 256) if worst_case else S * (2 * N + 64)  # 16 bit/symbol: ample for model data; retried at the worst case if exceeded
     if return_device == "async":  # no host synchronisation: caller inspects `sizes` (negative = error code) later
         packed = torch.empty(cap, dtype=torch.uint8, device=dev)
         check(L.icm_rans_encode_batch(tables.handle, symbols.data_ptr(), indexes.data_ptr(), S, N, work.data_ptr(),
@@ -244,11 +278,17 @@ class StreamDecoder:
               "icm_rans_decoder_step")
         return out
 
+    def fold_status(self, flag):
+        """flag (CUDA int32[1]) = min(flag, this decoder's per-stream statuses); asynchronous."""
+        check(lib().icm_rans_decoder_status_min(self.handle, flag.data_ptr(), stream_ptr()), "icm_rans_decoder_status_min")
+
     def check_status(self):
         st = np.zeros(self.n_streams, np.int32)
         check(lib().icm_rans_decoder_status(self.handle, st.ctypes.data_as(C.c_void_p), stream_ptr()), "icm_rans_decoder_status")
         if np.any(st == _ERR_BAD_INDEX):
             raise ValueError("decode: CDF index out of range")
+        if np.any(st < 0):
+            raise_for_status(int(st.min()), "decode (status handed over by the encoder)")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -188,7 +188,7 @@ class ChannelContextCodec(CompressionModel):
             t.record_stream(torch.cuda.current_stream())
         return t
 
-    def _compress_part(self, x, phase=None):
+    def _compress_part(self, x, phase=None, worst_case=False):
         """compress() of one micro-batch, fully asynchronous: device-resident streams.  `phase("begin"/"end")`
         brackets the throughput-bound part (transforms + slice loop); the rANS encoders run after "end"."""
         eb = self.entropy_bottleneck
@@ -208,8 +208,8 @@ class ChannelContextCodec(CompressionModel):
         _, sym, idx = self._slice_loop("compress", B, h, w, mean_sup, scale_sup, y=y)
         if phase:
             phase("end")
-        z_str = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device="async")
-        y_str = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device="async")
+        z_str = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device="async", worst_case=worst_case)
+        y_str = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device="async", worst_case=worst_case)
         return {"y": y_str, "z": z_str, "shape": (zh, zw), "retry": (sym, idx, z_sym, z_idx)}
 
     @torch.no_grad()
@@ -282,10 +282,19 @@ class ChannelContextCodec(CompressionModel):
                                coder_streams=jobs[0][2])
         xs = [self._hand_over(o[0]) for o in outs]
         try:
-            if not on_device:  # (status is a host read; the device-resident path leaves it to the caller)
+            if not on_device:
                 for _, decs in outs:
                     for d in decs:
                         d.check_status()
+            else:
+                # device-resident streams: the encoder's per-stream status (capacity / bad index; it became the decoder's
+                # status when the streams were handed over) and the decoders' own are folded into ONE word on the device
+                # and read once -- a failed encode must not decode zeros into a plausible-looking x_hat
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                for _, decs in outs:
+                    for d in decs:
+                        d.fold_status(flag)
+                ans.raise_for_status(int(flag.item()), f"{type(self).__name__}.decompress")
         finally:
             for _, decs in outs:
                 for d in decs:

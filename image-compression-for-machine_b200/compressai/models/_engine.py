@@ -70,10 +70,16 @@ class Engine:
         self.warm = False
 
     # ---------------------------------------------------------------------------------- weights
+    @staticmethod
+    def _versions(module):
+        """(data_ptr, _version) of every parameter of a holder: in-place edits (optimizer steps, weight.mul_) bump _version,
+        re-assignment changes data_ptr -- either invalidates the packed copy, like EntropyBottleneck.packed_params()."""
+        return tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=False))
+
     def packed(self, module, ps=0):
         key = (id(module), ps)
         hit = self._packed.get(key)
-        pk = hit[0] if hit is not None else None
+        pk = hit[0] if hit is not None and hit[2] == self._versions(module) else None
         if pk is None:
             if isinstance(module, torch.nn.Conv2d):
                 pk = PackedConv(module.weight, module.bias, module.stride[0], module.padding[0], ps)
@@ -86,15 +92,15 @@ class Engine:
                 pk = PackedConv(gamma, beta, 1, 0, 0)
             else:
                 raise TypeError(type(module))
-            self._packed[key] = (pk, module)  # holding the module keeps its id() from being reused
+            self._packed[key] = (pk, module, self._versions(module))  # holding the module keeps its id() from being reused
             torch.cuda.current_stream().synchronize()  # packed before any other stream may use it (micro-batches)
         return pk
 
     def f32(self, p):
         key = (id(p), "f32")
         hit = self._packed.get(key)
-        if hit is None:
-            hit = (p.detach().float().contiguous(), p)
+        if hit is None or hit[2] != (p.data_ptr(), p._version):
+            hit = (p.detach().float().contiguous(), p, (p.data_ptr(), p._version))
             self._packed[key] = hit
             torch.cuda.current_stream().synchronize()
         return hit[0]

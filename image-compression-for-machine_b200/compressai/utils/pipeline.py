@@ -32,16 +32,23 @@ class RoundTripPipeline:
     up to `lag` other jobs run beside them.  Without the chain all jobs start in lockstep, reach their coders
     together and leave the GPU idle (measured run-to-run spread 400-530 images/s)."""
 
-    def __init__(self, model, n_streams=12, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=8, chains=2):
+    def __init__(self, model, n_streams=12, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=8, chains=2, decode_priority=False):
         self.model = model
         self.decoder_streams_per_cta = int(decoder_streams_per_cta)
-        # The decoder's CTAs (~155 KB of shared memory) cannot share an SM with a persistent conv CTA (~200 KB); the
-        # conv grid leaves them room.  None = 148 - (jobs in their decode loop) * ceil(part / streams per CTA).
+        # SMs the persistent conv / MLP kernels may occupy.  0 = all: the conv kernel's tile scheduler is dynamic, so a CTA
+        # that finds its SM held by a decoder CTA (~190 KB of shared memory: they cannot share an SM) simply starts late
+        # and finds no tiles left.  None = the round-1 rule for a static scheduler: 148 - (jobs in their decode loop) *
+        # ceil(part / streams per CTA).
         self.conv_sm_limit = conv_sm_limit
         self.n_streams = int(n_streams)
         self.part = int(part)
         self.lag = max(0, min(int(lag), self.n_streams - 1))
         self.chains = max(0, int(chains))
+        # decode_priority: the latency-bound decode loop of a job (12 x {two conv stacks, a decoder step, a conv stack}, small
+        # kernels) runs on a high-priority twin of the job's stream, so that its CTAs are placed ahead of the queued CTAs of
+        # other jobs' throughput-bound kernels
+        self.decode_priority = bool(decode_priority)
+        self._hi = None
         self._streams = None
         self._decoders = {}
         self._pinned = {}
@@ -50,6 +57,7 @@ class RoundTripPipeline:
     def _setup(self, device):
         if self._streams is None or self._streams[0].device != device:
             self._streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)]
+            self._hi = [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.n_streams)] if self.decode_priority else None
             self._decoders = {}
 
     def _decoder_pair(self, slot, n):
@@ -88,6 +96,17 @@ class RoundTripPipeline:
 
     @torch.no_grad()
     def roundtrip(self, batches, host_io=False, out_host=None, keep_outputs=True):
+        """See _roundtrip.  The encoders write into buffers sized for 16 bit/symbol; if a stream outgrows that (the
+        folded device status says ICM_ERR_CAPACITY) the whole call is repeated with worst-case buffers."""
+        from compressai import ans
+
+        try:
+            return self._roundtrip(batches, host_io, out_host, keep_outputs, worst_case=False)
+        except ans.CapacityError:
+            torch.cuda.synchronize()
+            return self._roundtrip(batches, host_io, out_host, keep_outputs, worst_case=True)
+
+    def _roundtrip(self, batches, host_io, out_host, keep_outputs, worst_case):
         """compress + decompress every batch of `batches` ([B,3,H,W] CUDA tensors, or pinned host tensors with
         host_io=True).  Returns (x_hats, strings): x_hats per batch (CUDA, or written into `out_host`), strings per
         batch as [[y bytes...], [z bytes...]] when host_io else None.  keep_outputs=False drops each job's x_hat as soon as
@@ -104,8 +123,12 @@ class RoundTripPipeline:
             limit = max(sms // 2, sms - decoding * ((self.part + per - 1) // per))
         check(lib().icm_set_conv_sm_limit(int(limit)), "icm_set_conv_sm_limit")
         check(lib().icm_set_decoder_streams_per_cta(self.decoder_streams_per_cta), "icm_set_decoder_streams_per_cta")
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)  # min over every encoder size / decoder status of the call
         for st in self._streams:
             st.wait_stream(cur)
+            flag.record_stream(st)
+        for st in self._hi or ():
+            flag.record_stream(st)
         self._tokens = {}
         jobs = []
         for bi, x in enumerate(batches):
@@ -114,6 +137,8 @@ class RoundTripPipeline:
                 jobs.append((bi, lo, min(x.shape[0], lo + self.part)))
         results = [[] for _ in batches]
         pending, decoded = [], {}
+        from compressai import ans
+
         lag = self.lag if self.chains else 0
 
         def front(t):  # C phase + encoders + decode loop of job t
@@ -122,7 +147,7 @@ class RoundTripPipeline:
             x = batches[bi]
             with torch.cuda.stream(self._streams[slot]):
                 xd = x[lo:hi].to(dev, non_blocking=True) if host_io else x[lo:hi]
-                c = m._compress_part(xd, phase=self._phase(t % self.chains) if self.chains else None)
+                c = m._compress_part(xd, phase=self._phase(t % self.chains) if self.chains else None, worst_case=worst_case)
                 zh, zw = c["shape"]
                 y_str, z_str = c["y"], c["z"]
                 if host_io:  # streams leave for the host and come back, like bytes handed to a decoder
@@ -135,7 +160,22 @@ class RoundTripPipeline:
                     ev = torch.cuda.Event()
                     ev.record(self._streams[slot])  # both directions of the staging buffers are done after this
                     pending.append((ev, bi, hy, hsy, hz, hsz))
-                y_hat, _ = m._decode_part(y_str, z_str, hi - lo, zh, zw, True, decoders=self._decoder_pair(slot, hi - lo))
+                decs = self._decoder_pair(slot, hi - lo)
+                if self._hi is None:
+                    y_hat, _ = m._decode_part(y_str, z_str, hi - lo, zh, zw, True, decoders=decs)
+                    for d in decs:  # encoder errors travel with the streams into the decoder status
+                        d.fold_status(flag)
+                else:
+                    hs, ns = self._hi[slot], self._streams[slot]
+                    hs.wait_stream(ns)
+                    for tns in (*y_str, *z_str):
+                        tns.record_stream(hs)
+                    with torch.cuda.stream(hs):
+                        y_hat, _ = m._decode_part(y_str, z_str, hi - lo, zh, zw, True, decoders=decs)
+                        for d in decs:
+                            d.fold_status(flag)
+                    y_hat.record_stream(ns)
+                    ns.wait_stream(hs)
                 decoded[t] = (y_hat, zh, zw)
 
         def back(t):  # S phase of job t
@@ -163,7 +203,7 @@ class RoundTripPipeline:
                 for packed, sizes, dst in ((hy, hsy, strings[bi][0]), (hz, hsz, strings[bi][1])):
                     hs = sizes.tolist()
                     if min(hs[:-1]) < 0:
-                        raise RuntimeError("rANS encoder reported an error status (buffer capacity or bad index)")
+                        ans.raise_for_status(min(hs[:-1]), "RoundTripPipeline (encoder)")
                     raw, o = packed.numpy(), 0
                     for v in hs[:-1]:
                         dst.append(raw[o:o + v].tobytes())
@@ -182,6 +222,8 @@ class RoundTripPipeline:
                 cur.wait_stream(st)
             if host_io:
                 drain(True)
+            # one host read for the whole call: a failed encode (capacity, bad index) must not pass as a decoded image
+            ans.raise_for_status(int(flag.item()), "RoundTripPipeline")
         finally:
             check(lib().icm_set_conv_sm_limit(0), "icm_set_conv_sm_limit")
             check(lib().icm_set_decoder_streams_per_cta(0), "icm_set_decoder_streams_per_cta")

@@ -49,6 +49,7 @@ struct View {
 };
 static inline View as_view(const icm_view &v) { return View{(char *)v.ptr, v.sb, v.sc, v.sp}; }
 
+int *tile_counter(cudaStream_t st); // csrc/conv.cu: the dynamic tile scheduler's {next, finished} pair of this stream
 int sm_count();   // of the current device (cached per device)
 int current_device_ordinal();
 

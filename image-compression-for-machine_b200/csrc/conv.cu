@@ -18,6 +18,10 @@
 // sides of the codec see bit-identical means/scales (SURVEY.md §7 "Encoder/decoder determinism").
 #include "umma.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace icm {
 
 struct ConvParams {
@@ -38,6 +42,7 @@ struct ConvParams {
     const float *bias;
     const void *residual;
     void *out;
+    int *sched;              // {next tile to hand out beyond the first wave, CTAs finished}: this stream's tile counter
 };
 
 // The activation switch sits OUTSIDE the 16-element loop (one uniform branch per chunk): with it inside, the
@@ -72,11 +77,18 @@ __device__ __forceinline__ void apply_act16(float (&v)[16], int act)
 }
 
 constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
+constexpr int TQ = 4;                              // depth of the tile-id queue between the scheduler thread and its consumers
 constexpr int CONV_THREADS = (2 + EPI_WARPS) * 32; // TMA warp + MMA warp + epilogue warps
 
-// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA pipeline runs
-// across tile boundaries, and the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps
-// the loads and MMAs of tile i+1.
+// Persistent with a DYNAMIC tile scheduler: a CTA's first tile is blockIdx.x, every further tile comes from an atomic
+// counter (gridDim.x + atomicAdd).  The TMA thread is the scheduler: it fetches the tile id one tile ahead and hands
+// it to the MMA thread and the epilogue warps through a small mbarrier-guarded queue in shared memory.  A CTA that
+// starts late -- its SM was held by an rANS coder CTA of another stream, which cannot share an SM with this kernel's
+// ~200 KB of shared memory -- therefore finds no work left instead of delaying the launch by the tiles a static
+// round-robin would have reserved for it, so the grid never has to leave SMs unused "in case".  The last CTA to
+// finish resets the counter for the next launch on the stream.  Which CTA computes a tile does not affect its result
+// (no cross-tile reduction), so outputs stay bit-identical.  The TMA pipeline runs across tile boundaries, and the
+// accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ConvParams p)
 {
@@ -89,7 +101,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t *empty_bar = full_bar + MAX_STAGES;
     uint64_t *acc_full = empty_bar + MAX_STAGES; // [2] MMA -> epilogue
     uint64_t *acc_empty = acc_full + 2;          // [2] epilogue -> MMA
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *tq_full = acc_empty + 2;           // [TQ] scheduler (TMA thread) -> MMA thread + epilogue warps: s_tile[slot] is set
+    uint64_t *tq_empty = tq_full + TQ;           // [TQ] consumers -> scheduler
+    int *s_tile = reinterpret_cast<int *>(tq_empty + TQ); // [TQ] tile ids, -1 = no more tiles
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_tile + TQ);
     float *s_bias = reinterpret_cast<float *>(tmem_slot + 4); // [n_tiles * BN], zeros without a bias
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,6 +115,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
+        for (int a = 0; a < TQ; ++a) { mbar_init(&tq_full[a], 1); mbar_init(&tq_empty[a], EPI_WARPS + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += blockDim.x) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
@@ -132,9 +148,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int tile = blockIdx.x; // < total_tiles: the grid never exceeds the number of tiles
+            int slot = 0;
+            uint32_t qphase = 0;
+            while (true) {
+                mbar_wait(&tq_empty[slot], qphase ^ 1);
+                s_tile[slot] = tile < p.total_tiles ? tile : -1;
+                mbar_arrive(&tq_full[slot]); // release semantics: the id is visible to whoever observes the phase
+                if (++slot == TQ) { slot = 0; qphase ^= 1; }
+                if (tile >= p.total_tiles) break;
+                const int next = (int)gridDim.x + atomicAdd(p.sched, 1); // in flight while this tile's loads are issued
                 int n0, w0, h0, b;
                 tile_coords(tile, n0, w0, h0, b);
+                tile = next;
                 for (int it = 0; it < k_iters; ++it) {
                     const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
                     const int dy = tap / p.KW, dx = tap - dy * p.KW;
@@ -164,7 +190,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int slot = 0;
+            uint32_t qphase = 0;
+            while (true) {
+                mbar_wait(&tq_full[slot], qphase);
+                const int tile = *reinterpret_cast<volatile int *>(&s_tile[slot]);
+                mbar_arrive(&tq_empty[slot]); // only whether there is a tile matters here
+                if (++slot == TQ) { slot = 0; qphase ^= 1; }
+                if (tile < 0) break;
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1); // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
@@ -293,7 +326,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
         };
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int slot = 0;
+        uint32_t qphase = 0;
+        while (true) {
+            mbar_wait(&tq_full[slot], qphase);
+            const int tile = *reinterpret_cast<volatile int *>(&s_tile[slot]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tq_empty[slot]);
+            if (++slot == TQ) { slot = 0; qphase ^= 1; }
+            if (tile < 0) break;
             int n0, w0, h0, b;
             tile_coords(tile, n0, w0, h0, b);
             const int oh = h0 + th, ow = w0 + tw;
@@ -336,6 +377,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+    if (threadIdx.x == 0) { // every CTA has drawn its last tile id before it counts itself as finished
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------ weight packing
@@ -365,6 +412,31 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, int Cout, int Ci
 }
 
 // ------------------------------------------------------------------------------------ host side
+// Tile counter of the dynamic scheduler: {next, finished}, one pair per (device, stream).  Launches on one stream run
+// in order and the last CTA of a launch zeroes the pair, so a single pair per stream is enough; launches on different
+// streams never share one.  Entries live for the life of the process (streams are few and long-lived here).
+int *tile_counter(cudaStream_t st)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, int *> slots;
+    const std::pair<int, cudaStream_t> key(current_device_ordinal(), st);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = slots.find(key);
+    if (it != slots.end()) return it->second;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+        set_error("tile_counter: first use of a stream inside a graph capture (run the path once before capturing)");
+        return nullptr;
+    }
+    int *d = nullptr;
+    if (cudaMalloc(&d, 256) != cudaSuccess || cudaMemset(d, 0, 256) != cudaSuccess) { // cudaMemset: synchronous, done before any launch uses it
+        set_error("tile_counter: cudaMalloc failed");
+        return nullptr;
+    }
+    slots[key] = d;
+    return d;
+}
+
 static int pick_tile_w_log2(int Ho, int Wo)
 {
     long long best = -1;
@@ -382,10 +454,9 @@ static int pick_tile_w_log2(int Ho, int Wo)
 
 using namespace icm;
 
-// Cap on the number of persistent CTAs (= SMs) icm_conv2d may occupy, 0 = all.  Used when other streams run
-// the rANS decoder at the same time: its CTAs hold ~155 KB of shared memory each and cannot share an SM with
-// a conv CTA, so the conv grid leaves them room instead of queueing behind them (tiles are assigned to the
-// persistent CTAs statically, so a CTA that starts late delays the whole launch).
+// Cap on the number of persistent CTAs (= SMs) icm_conv2d may occupy, 0 = all.  With the dynamic tile scheduler a
+// launch no longer has to leave room for the rANS coder CTAs of other streams; a pipeline may still cap its
+// throughput-bound launches so that a few SMs stay free for latency-bound ones.
 extern "C" int icm_set_conv_sm_limit(int n_sms)
 {
     ICM_CHECK_ARG(n_sms >= 0, "icm_set_conv_sm_limit: negative limit");
@@ -477,7 +548,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.n_tiles = (a->Cout + p.BN - 1) / p.BN;
     const size_t bias_bytes = (size_t)p.n_tiles * p.BN * 4;
     ICM_CHECK_ARG(bias_bytes <= 16 * 1024, "icm_conv2d: Cout=%d too wide for the bias staging area", a->Cout);
-    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4) * 8 + 16 + bias_bytes;
+    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4 + 2 * TQ) * 8 + TQ * 4 + 16 + bias_bytes;
     static PerDeviceSmem configured;
     if (configured.needs(smem_bytes)) {
         ICM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -487,6 +558,8 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.total_tiles = (int)(m_tiles * p.n_tiles);
     auto magic = [](int d) -> unsigned long long { return d <= 1 ? 0ull : ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; };
     p.fd_n = magic(p.n_tiles); p.fd_w = magic(p.tiles_w); p.fd_h = magic(p.tiles_h);
+    p.sched = tile_counter(as_stream(stream));
+    if (!p.sched) return ICM_ERR_CUDA;
     const int max_ctas = persistent_grid_limit();
     const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
     conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);

@@ -28,6 +28,8 @@
 #include "common.cuh"
 #include "rans_lane.cuh"
 
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -289,6 +291,16 @@ __global__ void rans_set_streams_kernel(const int32_t *__restrict__ sizes, int n
         }
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
+}
+
+// flag = min(flag, min(values)): folds encoder sizes / decoder statuses (negative = ICM_ERR_*) into one word that the
+// host reads once per round trip instead of once per stream
+__global__ void __launch_bounds__(256) min_i32_kernel(const int32_t *__restrict__ v, long long n, int32_t *__restrict__ flag)
+{
+    int32_t m = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = min(m, v[i]);
+    for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m < 0) atomicMin(flag, m);
 }
 
 // (3) pack: exclusive scan of sizes (one warp) + copy
@@ -853,6 +865,8 @@ extern "C" int icm_rans_encode_batch(const icm_tables *t, const int32_t *d_symbo
     ICM_CHECK_ARG(((uintptr_t)d_packed & 3) == 0 && ((uintptr_t)d_work & 255) == 0, "icm_rans_encode_batch: misaligned buffers");
     ICM_CHECK_ARG(t->device == current_device(), "icm_rans_encode_batch: tables were created on device %d", t->device);
     cudaStream_t st = as_stream(stream);
+    static const bool skip = getenv("ICM_DEBUG_SKIP_CODERS") != nullptr; // profiling aid: what does the pipeline do without the coders?
+    if (skip) { ICM_CUDA(cudaMemsetAsync(d_sizes, 0, (size_t)(n_streams + 1) * 4, st)); return ICM_OK; }
     const EncLayout L = enc_layout(n_streams, n_per_stream);
     char *w = (char *)d_work;
     Record *rec = (Record *)(w + L.rec);
@@ -972,6 +986,8 @@ extern "C" int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, c
     ICM_CHECK_ARG(t->device == dev && d->device == dev, "icm_rans_decoder_step: tables (device %d) / decoder (device %d) used on device %d",
                   t->device, d->device, dev);
     if (n_per_stream == 0) return ICM_OK;
+    static const bool skip = getenv("ICM_DEBUG_SKIP_CODERS") != nullptr;
+    if (skip) { ICM_CUDA(cudaMemsetAsync(d_out, 0, (size_t)d->n_streams * n_per_stream * 4, as_stream(stream))); return ICM_OK; }
     const int S = d->n_streams;
     int warps = g_dec_warps;
     if (warps == 0) warps = S <= sm_count() / 2 ? 1 : (S <= sm_count() ? 2 : 4);
@@ -994,6 +1010,21 @@ extern "C" int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, c
         t->dev, S, d->d_words, d->d_word_off, d->d_nwords, d->d_state, d->d_pos, d_indexes, n_per_stream, d_out, d->d_status);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
+}
+
+extern "C" int icm_min_i32(const int32_t *d_values, int64_t n, int32_t *d_flag, void *stream)
+{
+    ICM_CHECK_ARG(d_values && d_flag && n >= 0, "icm_min_i32: bad arguments");
+    if (n == 0) return ICM_OK;
+    min_i32_kernel<<<(unsigned)min((long long)((n + 255) / 256), 64LL), 256, 0, as_stream(stream)>>>(d_values, n, d_flag);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_rans_decoder_status_min(icm_rans_decoder *d, int32_t *d_flag, void *stream)
+{
+    ICM_CHECK_ARG(d && d_flag, "icm_rans_decoder_status_min: null argument");
+    return icm_min_i32(d->d_status, d->n_streams, d_flag, stream);
 }
 
 extern "C" int icm_rans_decoder_status(icm_rans_decoder *d, int32_t *h_status, void *stream)

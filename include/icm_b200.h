@@ -198,8 +198,14 @@ int icm_layernorm(const float *d_in, const float *d_gamma, const float *d_beta, 
 /* fp32 -> bf16 copy of a [rows, C] block with row pitches (elements); C % 4 == 0. */
 int icm_cast_bf16(const float *d_in, int64_t rows, int C, int64_t in_pitch, void *d_out, int64_t out_pitch, void *stream);
 
-/* Per-stream status of a decoder (0 or ICM_ERR_BAD_INDEX); synchronises the stream. */
+/* Per-stream status of a decoder (0, ICM_ERR_BAD_INDEX, or the error its stream's encoder reported when the streams
+ * were handed over on the device); synchronises the stream. */
 int icm_rans_decoder_status(icm_rans_decoder *d, int32_t *h_status, void *stream);
+/* Asynchronous form for pipelines: *d_flag = min(*d_flag, statuses) / min(*d_flag, d_values[0..n)), so that one
+ * device word collects the encoder sizes (negative = ICM_ERR_*) and decoder statuses of a whole round trip and the
+ * host reads it once.  The reference has nothing to report here (compiled-out asserts, SURVEY.md 8b "Errors"). */
+int icm_rans_decoder_status_min(icm_rans_decoder *d, int32_t *d_flag, void *stream);
+int icm_min_i32(const int32_t *d_values, int64_t n, int32_t *d_flag, void *stream);
 
 /* T4 core: softmax(q k^T * scale + bias[rel_idx] + mask) v per (window, head) on a qkv tensor
  *     bf16 [B, H, W, 3C] (feature order s*C + h*hd + d, stf.py:97), writing bf16 [B, H, W, C] in token

@@ -300,8 +300,64 @@ def stf_full_golden():
     print("stf_full:", out)
 
 
+def eval_golden():
+    """The reference's OWN `inference()` and `psnr()` (compressai/utils/eval_model/__main__.py:78-81, 97-140), executed
+    from their unmodified source text on the reference STF: pad-to-64 / compress / decompress / crop / psnr / bpp of an
+    image whose size is not a multiple of 64.  The module itself cannot be imported here (pytorch_msssim, pycocotools,
+    detectron2, ptflops ... at its top), so the two function definitions are cut out of the file with `ast` and
+    exec'ed; `reconstruct` (a PNG write through torchvision) is replaced by a no-op."""
+    import ast
+    import math
+    import time
+
+    import torch.nn.functional as F
+
+    path = os.path.join(refshim.REF, "compressai", "utils", "eval_model", "__main__.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "F": F, "math": math, "os": os, "time": time, "reconstruct": lambda *a, **k: None}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("psnr", "inference"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    h = refshim.install("binary")
+    torch.manual_seed(0)
+    m = h["stf"].SymmetricalTransFormer().eval()
+    m.load_state_dict(weights.seeded_state_dict(m.state_dict(), seed=0, stress=True))
+    m.update(force=True)
+    x = weights.seeded_image((3, 100, 150), seed=21)
+    captured = {}
+    orig_c, orig_d = m.compress, m.decompress
+
+    def cap_c(xp):
+        captured["x_padded_shape"] = list(xp.shape)
+        captured["enc"] = orig_c(xp)
+        return captured["enc"]
+
+    def cap_d(strings, shape):
+        captured["dec"] = orig_d(strings, shape)
+        captured["x_hat_padded"] = captured["dec"]["x_hat"].clone()
+        return captured["dec"]
+
+    m.compress, m.decompress = cap_c, cap_d
+    import tempfile
+
+    rv = ns["inference"](m, x, "img.png", tempfile.mkdtemp(prefix="recon_"))
+    enc = captured["enc"]
+    np.savez_compressed(
+        os.path.join(GOLD, "eval_small.npz"),
+        psnr=np.float64(rv["psnr"]), bpp=np.float64(rv["bpp"]), x_padded_shape=np.asarray(captured["x_padded_shape"]),
+        shape=np.asarray(list(enc["shape"])), y_string=np.frombuffer(enc["strings"][0][0], np.uint8),
+        z_string=np.frombuffer(enc["strings"][1][0], np.uint8), x_hat_padded=captured["x_hat_padded"].numpy().astype(np.float32),
+        x_hat=captured["dec"]["x_hat"].numpy().astype(np.float32))
+    print("eval_small: psnr %.4f bpp %.4f padded %s y %d B z %d B" % (rv["psnr"], rv["bpp"], captured["x_padded_shape"],
+                                                                    len(enc["strings"][0][0]), len(enc["strings"][1][0])))
+    refshim.uninstall(h)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["stf_full"]:
+    if sys.argv[1:] == ["eval"]:
+        eval_golden()
+    elif sys.argv[1:] == ["stf_full"]:
         stf_full_golden()
     elif sys.argv[1:] == ["cnn"]:
         cnn_golden()
@@ -312,3 +368,4 @@ if __name__ == "__main__":
         cnn_golden()
         cnn2_full_golden()
         stf_full_golden()
+        eval_golden()
