@@ -87,6 +87,9 @@ class Profile:
         if name == "icm_swin_mlp":  # two products rows x 4C x C
             rows, Cc = args[6], args[7]
             return 2.0 * 2.0 * rows * 4 * Cc * Cc
+        if name == "icm_swin_block":  # qkv + proj (4 C^2) and the MLP (8 C^2) per token, plus the 16x16x16 attention products
+            rows, Cc, parts = args[1] * args[2] * args[3], args[4], args[8]
+            return 2.0 * rows * Cc * ((4 * Cc + 2 * 16) * (parts & 1) + 8 * Cc * ((parts >> 1) & 1))
         return 0.0
 
     def summary(self):
@@ -149,6 +152,7 @@ def _load():
         "icm_eb_process": (I, [I, View, I, I, I64, P, F, P, P, View, View, View, P]),
         "icm_conv2d": (I, [C.POINTER(ConvArgs), P]),
         "icm_swin_mlp": (I, [P, P, P, P, P, P, I64, I, P]),
+        "icm_swin_block": (I, [P, I, I, I, I, I, I, I, I] + [P] * 14),
         "icm_set_conv_sm_limit": (I, [I]),
         "icm_pack_conv_weight": (I, [P, I, I, I, I, I, I, I, P, P]),
         "icm_layernorm": (I, [P, P, P, P, I, I64, I, I, I, I, I, P]),

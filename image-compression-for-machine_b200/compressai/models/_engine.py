@@ -165,9 +165,22 @@ class Engine:
         return out
 
     # ---------------------------------------------------------------------------------- Swin pieces
+    fused_block = True  # icm_swin_block for C in (48, 96): one pass over the residual stream instead of six launches
+
     def swin_block(self, x, B, H, W, blk, shifted):
         """x: fp32 tokens [B*H*W, C], updated in place (stf.py:149-199)."""
         Cc = x.shape[1]
+        if self.fused_block and Cc in (48, 96) and blk.window_size == 4 and x.is_contiguous() and H % 4 == 0 and W % 4 == 0:
+            at, mlp = blk.attn, blk.mlp
+            qkv, proj, f1, f2 = self.packed(at.qkv), self.packed(at.proj), self.packed(mlp.fc1), self.packed(mlp.fc2)
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            check(lib().icm_swin_block(x.data_ptr(), B, H, W, Cc, at.num_heads, blk.window_size, blk.window_size // 2 if shifted else 0, 3,
+                                       qkv.w.data_ptr(), ptr(qkv.bias), proj.w.data_ptr(), ptr(proj.bias),
+                                       self.f32(at.relative_position_bias_table).data_ptr(),
+                                       self.f32(blk.norm1.weight).data_ptr(), self.f32(blk.norm1.bias).data_ptr(),
+                                       f1.w.data_ptr(), ptr(f1.bias), f2.w.data_ptr(), ptr(f2.bias),
+                                       self.f32(blk.norm2.weight).data_ptr(), self.f32(blk.norm2.bias).data_ptr(), stream_ptr()), "icm_swin_block")
+            return x
         xn = self.layernorm(x, blk.norm1)
         qkv = self.linear(xn, self.packed(blk.attn.qkv))
         ao = self.window_attention(qkv, B, H, W, Cc, blk.attn.num_heads, blk.window_size, blk.window_size // 2 if shifted else 0,

@@ -187,6 +187,17 @@ int icm_set_conv_sm_limit(int n_sms);
  * icm_conv2d launches (ICM_ACT_GELU, then residual). */
 int icm_swin_mlp(const void *d_h_bf16, const void *d_w1_packed, const float *d_b1, const void *d_w2_packed, const float *d_b2,
                  float *d_x, int64_t rows, int C, void *stream);
+/* Whole Swin block in one pass over the residual stream, for the narrow stages C in {48, 96} (window 4, head_dim 16;
+ * stf.py:149-199): parts & 1: x += proj(attention(qkv(LayerNorm1(x)))); parts & 2: x += fc2(GELU(fc1(LayerNorm2(x)))).
+ * x fp32 [B*H*W, C] in place; one warp per 4x4 window, every intermediate in registers (csrc/swin_fused.cu).
+ * Weights: bf16 rows as icm_pack_conv_weight leaves a 1x1 layer ([Cout][Cin padded to 64]); biases / LayerNorm
+ * parameters / relative-position table [49][heads] fp32.  Replaces icm_layernorm + icm_conv2d (qkv) +
+ * icm_window_attention + icm_conv2d (proj) + icm_layernorm + icm_swin_mlp at these widths. */
+int icm_swin_block(float *d_x, int B, int H, int W, int C, int heads, int window, int shift, int parts,
+                   const void *d_w_qkv, const float *d_b_qkv, const void *d_w_proj, const float *d_b_proj,
+                   const float *d_rel_table, const float *d_ln1_g, const float *d_ln1_b,
+                   const void *d_w_fc1, const float *d_b_fc1, const void *d_w_fc2, const float *d_b_fc2,
+                   const float *d_ln2_g, const float *d_ln2_b, void *stream);
 int icm_pack_conv_weight(const float *d_w_oihw, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,
                          int pixel_shuffle, void *d_out_bf16, void *stream);
 

@@ -198,3 +198,61 @@ def test_fused_swin_mlp_is_bit_identical_to_two_launches(eng, C, M):
         h = F.gelu(F.linear(xn.float().cpu(), _bf(mlp.fc1.weight.cpu()), mlp.fc1.bias.cpu()))
         ref = x0 + F.linear(_bf(h), _bf(mlp.fc2.weight.cpu()), mlp.fc2.bias.cpu())
     _close(xa, ref, rtol=5e-3, atol=5e-3)
+
+
+@pytest.mark.parametrize("C,heads,shifted,B,H,W", [(48, 3, False, 2, 8, 12), (48, 3, True, 2, 8, 12), (96, 6, True, 1, 12, 8), (96, 6, False, 3, 4, 4),
+                                                   (48, 3, True, 1, 64, 32)])
+def test_fused_swin_block_against_the_fp32_block_and_the_six_launch_path(eng, C, heads, shifted, B, H, W):
+    """icm_swin_block (csrc/swin_fused.cu: LayerNorm -> qkv -> window attention -> proj -> +x -> LayerNorm -> MLP -> +x in
+    registers, one warp per window) against the oracle's fp32 restatement of SwinTransformerBlock.forward (stf.py:149-199)
+    and against the six-launch path it replaces (same bf16 rounding points; only the accumulation order differs)."""
+    from oracle import stf_ref
+
+    g = torch.Generator().manual_seed(C * 7 + heads + int(shifted))
+    blk = torch.nn.Module()
+    blk.window_size = 4
+    blk.norm1, blk.norm2 = torch.nn.LayerNorm(C), torch.nn.LayerNorm(C)
+    blk.attn = torch.nn.Module()
+    blk.attn.num_heads = heads
+    blk.attn.qkv, blk.attn.proj = torch.nn.Linear(C, 3 * C), torch.nn.Linear(C, C)
+    blk.attn.relative_position_bias_table = torch.nn.Parameter(torch.randn(49, heads, generator=g) * 0.5)
+    blk.mlp = torch.nn.Module()
+    blk.mlp.fc1, blk.mlp.fc2 = torch.nn.Linear(C, 4 * C), torch.nn.Linear(4 * C, C)
+    with torch.no_grad():
+        for name, prm in blk.named_parameters():
+            if "relative_position" in name:
+                continue
+            if "norm" in name:
+                prm.copy_((1.0 if name.endswith("weight") else 0.0) + 0.1 * torch.randn(prm.shape, generator=g))
+            else:
+                prm.copy_(torch.randn(prm.shape, generator=g) * (0.1 if prm.dim() == 1 else 1.0 / prm.shape[1] ** 0.5))
+    x0 = torch.randn(B * H * W, C, generator=g) * 2 + 0.3
+    # fp32 reference: the oracle's swin_block on [B, L, C] tokens
+    p = {k: v.detach() for k, v in blk.state_dict().items()}
+    p["attn.relative_position_index"] = stf_ref.rel_pos_index(4)
+    mask = stf_ref.shift_mask(H, W, 4) if shifted else None
+    ref = stf_ref.swin_block(x0.reshape(B, H * W, C), H, W, p, heads, shifted, mask).reshape(-1, C)
+    blk = blk.cuda()
+    xa, xb = x0.cuda().clone(), x0.cuda().clone()
+    eng.fused_block = True
+    eng.swin_block(xa, B, H, W, blk, shifted)
+    eng.fused_block = False
+    eng.swin_block(xb, B, H, W, blk, shifted)
+    eng.fused_block = True
+    torch.cuda.synchronize()
+    _close(xa, ref, rtol=2e-2, atol=2e-2)   # bf16 operands
+    _close(xa, xb, rtol=1e-2, atol=1e-2)    # same rounding points as the unfused path; the MLP's GELU is the tanh form here and
+                                            # the erf-polynomial form there (|difference| <= 5e-4 before the bf16 rounding)
+    # the halves on their own (C = 96 always runs them as two launches)
+    from compressai._native import check, lib, stream_ptr
+
+    xc = x0.cuda().clone()
+    at, mlp = blk.attn, blk.mlp
+    qkv, proj, f1, f2 = eng.packed(at.qkv), eng.packed(at.proj), eng.packed(mlp.fc1), eng.packed(mlp.fc2)
+    args = (qkv.w.data_ptr(), qkv.bias.data_ptr(), proj.w.data_ptr(), proj.bias.data_ptr(), eng.f32(at.relative_position_bias_table).data_ptr(),
+            eng.f32(blk.norm1.weight).data_ptr(), eng.f32(blk.norm1.bias).data_ptr(), f1.w.data_ptr(), f1.bias.data_ptr(), f2.w.data_ptr(),
+            f2.bias.data_ptr(), eng.f32(blk.norm2.weight).data_ptr(), eng.f32(blk.norm2.bias).data_ptr(), stream_ptr())
+    for parts in (1, 2):
+        check(lib().icm_swin_block(xc.data_ptr(), B, H, W, C, heads, 4, 2 if shifted else 0, parts, *args))
+    torch.cuda.synchronize()
+    assert torch.equal(xc, xa)
