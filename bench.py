@@ -178,13 +178,13 @@ def main():
     ap.add_argument("--weights", default="default", choices=sorted(WEIGHTS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=12, help="CUDA streams of the codec pipeline")
+    ap.add_argument("--streams", type=int, default=-1, help="CUDA streams of the codec pipeline (-1 = automatic: ~384 images in flight, 12..32)")
     ap.add_argument("--part", type=int, default=32, help="images per pipeline job")
     ap.add_argument("--dec-per-cta", type=int, default=8, help="rANS decoder streams per CTA in the pipeline (1, 2, 4, 8, 16)")
-    ap.add_argument("--lag", type=int, default=8, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag")
+    ap.add_argument("--lag", type=int, default=-1, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag (-1 = automatic)")
     ap.add_argument("--chains", type=int, default=2, help="pipeline: jobs allowed in a throughput-bound phase at once (0 = unordered)")
     ap.add_argument("--conv-sms", type=int, default=0, help="cap on SMs used by the conv kernel (0 = all: its tile scheduler is dynamic)")
-    ap.add_argument("--decode-priority", type=int, default=1, help="pipeline: run each job's decode loop on a high-priority stream")
+    ap.add_argument("--decode-priority", type=int, default=-1, help="pipeline: run each job's decode loop on a high-priority stream (-1 = automatic)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch images per GPU; strong: --batch images in total")
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-weights sub-record")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency sub-record")
@@ -193,6 +193,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    b_gpu = args.batch // world if args.scaling == "strong" and args.batch % world == 0 else args.batch
+    # Pipeline depth: the two coders are latency-bound (~35 ms + ~50 ms per job whatever its size), so throughput needs
+    # ~400 images in flight; small per-GPU batches (strong scaling: 8 images per GPU at N = 8) therefore need more,
+    # smaller jobs in flight.  The streams (and their high-priority twins) must fit the 32 hardware queues.
+    part_eff = max(1, min(args.part, b_gpu))
+    if args.streams < 0:
+        args.streams = max(12, min(32, -(-384 // part_eff)))
+    if args.decode_priority < 0:
+        args.decode_priority = 1 if args.streams <= 16 else 0
+    if args.lag < 0:
+        args.lag = 8 if args.streams <= 12 else args.streams - 3
     if args.scaling == "strong":
         if args.batch % world:
             raise SystemExit(f"--scaling strong: --batch {args.batch} is not a multiple of the {world} GPUs")
