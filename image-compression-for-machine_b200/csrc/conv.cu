@@ -8,7 +8,7 @@
 //              is TMA's out-of-bounds zero fill, stride-2 convolutions use the tensor map's element strides)
 //              and one 2-D box of the packed weights, both landing 128B-swizzled in shared memory;
 //   warp 1     allocates TMEM and issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM);
-//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating 16-column chunks): tcgen05.ld the
+//   warps 2-17 epilogue (four warps per TMEM lane quarter, taking 16-column chunks in turn): tcgen05.ld the
 //              accumulator rows, bias + activation (+ residual) in registers, vectorised stores (optionally
 //              with the PixelShuffle permutation folded into the address).
 // Shared memory and TMEM are sized so that two (small-K layers: up to four) CTAs share an SM: the epilogue of
