@@ -35,6 +35,11 @@ class ConvArgs(C.Structure):
     ]
 
 
+class ConvGroups(C.Structure):
+    _fields_ = [("groups", C.c_int), ("in_images", C.c_int), ("weight_group_rows", C.c_int64), ("bias_group_stride", C.c_int64),
+                ("out_group_stride", C.c_int64), ("in_image_offset", C.c_int * 16), ("tail_channel", C.c_int * 16)]
+
+
 _lib = None
 _profile = None  # a Profile instance while per-call CUDA-event timing is switched on (bench.py)
 
@@ -79,11 +84,12 @@ class Profile:
 
     @staticmethod
     def _work(name, args):
-        if name == "icm_conv2d":  # algorithmic FLOPs: 2 * output pixels * Cout * taps * Cin
+        if name in ("icm_conv2d", "icm_conv2d_grouped"):  # algorithmic FLOPs: 2 * output pixels * Cout * taps * Cin (x groups)
             a = args[0]._obj
             Ho = (a.H + 2 * a.pad - a.KH) // a.stride + 1
             Wo = (a.W + 2 * a.pad - a.KW) // a.stride + 1
-            return 2.0 * a.B * Ho * Wo * a.Cout * a.KH * a.KW * a.Cin
+            G = args[1]._obj.groups if name == "icm_conv2d_grouped" else 1
+            return 2.0 * G * a.B * Ho * Wo * a.Cout * a.KH * a.KW * a.Cin
         if name == "icm_swin_mlp":  # two products rows x 4C x C
             rows, Cc = args[6], args[7]
             return 2.0 * 2.0 * rows * 4 * Cc * Cc
@@ -151,6 +157,7 @@ def _load():
         "icm_add_lrp": (I, [View, View, I, I, I64, View, View, P]),
         "icm_eb_process": (I, [I, View, I, I, I64, P, F, P, P, View, View, View, P]),
         "icm_conv2d": (I, [C.POINTER(ConvArgs), P]),
+        "icm_conv2d_grouped": (I, [C.POINTER(ConvArgs), C.POINTER(ConvGroups), P]),
         "icm_swin_mlp": (I, [P, P, P, P, P, P, I64, I, P]),
         "icm_swin_block": (I, [P, I, I, I, I, I, I, I, I] + [P] * 14),
         "icm_set_conv_sm_limit": (I, [I]),

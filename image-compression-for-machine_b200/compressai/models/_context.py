@@ -55,19 +55,37 @@ class ChannelContextCodec(CompressionModel):
         if x.shape[2] % 64 or x.shape[3] % 64:
             raise ValueError("H and W must be multiples of 64 (pad like the reference eval does, eval_model/__main__.py:103-115)")
 
+    # Grouped launches (icm_conv2d_grouped).  Stacks that the reference's data flow leaves independent share a launch:
+    # h_mean_s || h_scale_s, cc_mean[i] || cc_scale[i], and -- because only the FIRST max_support_slices decoded slices are
+    # ever used as support (stf.py:612, cnn.py:162) -- every stack of the slices i >= max_support_slices.  Those slices are
+    # then quantised / decoded / LRP-corrected in one step as well (2 * (num_slices - max_support) conv stacks, one entropy
+    # launch, one rANS step and one grouped LRP stack instead of num_slices - max_support rounds of each).  Per output
+    # element the arithmetic is the ungrouped kernel's, so symbols, indexes and bit-strings are unchanged.
+    grouped = True
+
+    def _tail_grouped(self):
+        """Slices >= max_support in one step: needs the LRP stacks' [support | y_hat_i] split on a 64-channel chunk boundary."""
+        return self.grouped and self.num_slices > self.max_support_slices + 1 and (self.latent_channels + SLICE * self.max_support_slices) % 64 == 0
+
     def _hyper_synthesis(self, z_hat_bf16, B, zh, zw):
-        """h_mean_s / h_scale_s (stf.py:604-605) written straight into channels [0, M) of the support buffers."""
+        """h_mean_s / h_scale_s (stf.py:604-605) written straight into channels [0, M) of the support buffers:
+        sup[0] = mean support, sup[1] = scale support, [2, B*P, pitch] with one 32-channel slot per slice behind the M
+        hyper-prior channels (all num_slices slots when the tail slices are grouped, else max_support + 1)."""
         e = self._engine
         P = 16 * zh * zw
         M = self.latent_channels
-        mean_sup = torch.zeros((B * P, M + SLICE * (self.max_support_slices + 1)), dtype=torch.bfloat16, device=z_hat_bf16.device)
-        scale_sup = torch.zeros((B * P, M + SLICE * self.max_support_slices), dtype=torch.bfloat16, device=z_hat_bf16.device)
-        e.conv_stack(z_hat_bf16, B, zh, zw, self.h_mean_s, final_dtype=OUT_BF16, final_out=mean_sup)
-        e.conv_stack(z_hat_bf16, B, zh, zw, self.h_scale_s, final_dtype=OUT_BF16, final_out=scale_sup)
-        return mean_sup, scale_sup
+        slots = self.num_slices if self._tail_grouped() else self.max_support_slices + 1
+        sup = torch.zeros((2, B * P, M + SLICE * slots), dtype=torch.bfloat16, device=z_hat_bf16.device)
+        if self.grouped:
+            e.conv_stack_group(z_hat_bf16, B, zh, zw, [self.h_mean_s, self.h_scale_s], B, [0, 0], final_dtype=OUT_BF16,
+                               final_out=sup, final_out_group_stride=sup.shape[1] * sup.shape[2])
+        else:
+            e.conv_stack(z_hat_bf16, B, zh, zw, self.h_mean_s, final_dtype=OUT_BF16, final_out=sup[0])
+            e.conv_stack(z_hat_bf16, B, zh, zw, self.h_scale_s, final_dtype=OUT_BF16, final_out=sup[1])
+        return sup[0], sup[1]
 
     def _slice_loop(self, mode, B, h, w, mean_sup, scale_sup, y=None, decoder=None, y_lik=None):
-        """The 12-slice channel-conditional loop (stf.py:611-631, 703-726, 754-776).
+        """The channel-conditional slice loop (stf.py:611-631, 703-726, 754-776).
 
         mode "compress": returns (y_hat, symbols, indexes) with symbols/indexes int32 [B, M*P] in stream order;
         mode "forward":  fills y_lik (NCHW fp32) and returns (y_hat, None, None);
@@ -77,7 +95,13 @@ class ChannelContextCodec(CompressionModel):
         P = h * w
         L = lib()
         st = stream_ptr()
-        M, Z = self.latent_channels, SLICE
+        M, Z, S, N = self.latent_channels, SLICE, self.max_support_slices, self.num_slices
+        pitch = mean_sup.shape[-1]
+        sup = None
+        if self.grouped:  # both planes of the [2, B*P, pitch] buffer _hyper_synthesis made
+            assert scale_sup.data_ptr() == mean_sup.data_ptr() + B * P * pitch * 2 and scale_sup.shape[-1] == pitch
+            sup = torch.as_strided(mean_sup, (2 * B * P, pitch), (pitch, 1))
+        tail = self._tail_grouped() and pitch == M + Z * N
         y_hat = torch.empty((B * P, M), dtype=torch.float32, device=dev)
         table = gc.scale_table_device(dev)
         sym = idx = None
@@ -86,33 +110,58 @@ class ChannelContextCodec(CompressionModel):
             idx = torch.empty_like(sym)
         elif mode == "decompress":
             gct = gc.device_tables()
-            idx_s = torch.empty((B, Z * P), dtype=torch.int32, device=dev)
-            sym_s = torch.empty_like(idx_s)
-        for i in range(self.num_slices):
-            k = min(i, self.max_support_slices)
-            mu, _, _ = e.conv_stack(mean_sup, B, h, w, self.cc_mean_transforms[i])
-            sc, _, _ = e.conv_stack(scale_sup, B, h, w, self.cc_scale_transforms[i])
-            v_mu, v_sc = view_bcp(mu, B, Z, P), view_bcp(sc, B, Z, P)
-            v_hat = view_bcp(y_hat, B, Z, P, Z * i)
-            v_slot = view_bcp(mean_sup, B, Z, P, M + Z * k)  # pre-LRP ŷ_i, input of lrp_transforms[i]
+        # steps: (first slice, number of slices)
+        steps = [(i, 1) for i in range(S if tail else N)] + ([(S, N - S)] if tail else [])
+        for i, n in steps:
+            k = min(i, S)
+            C = Z * n
+            if n > 1:    # every cc stack of the slices >= S: same support, 2n groups
+                musc = torch.empty((B * P, 2 * C), dtype=torch.float32, device=dev)
+                e.conv_stack_group(sup, B, h, w, list(self.cc_mean_transforms[i:]) + list(self.cc_scale_transforms[i:]), 2 * B,
+                                   [0] * n + [B] * n, final_out=musc, final_out_group_stride=Z, cin=M + Z * k)
+                v_mu, v_sc = view_bcp(musc, B, C, P), view_bcp(musc, B, C, P, C)
+            elif self.grouped:
+                musc, _, _ = e.conv_stack_group(sup, B, h, w, [self.cc_mean_transforms[i], self.cc_scale_transforms[i]], 2 * B, [0, B],
+                                                cin=M + Z * k)
+                v_mu, v_sc = view_bcp(musc[0], B, C, P), view_bcp(musc[1], B, C, P)
+            else:
+                mu, _, _ = e.conv_stack(mean_sup, B, h, w, self.cc_mean_transforms[i])
+                sc, _, _ = e.conv_stack(scale_sup, B, h, w, self.cc_scale_transforms[i])
+                v_mu, v_sc = view_bcp(mu, B, C, P), view_bcp(sc, B, C, P)
+            v_hat = view_bcp(y_hat, B, C, P, Z * i)
+            # pre-LRP ŷ_i, input of lrp_transforms[i]: slot i when every slice has one, else the slot behind the support slices
+            v_slot = view_bcp(mean_sup, B, C, P, M + Z * (i if tail else k))
             if mode == "compress":
-                check(L.icm_gc_quantize_index(view_bcp(y, B, Z, P, Z * i), v_mu, v_sc, B, Z, P, table.data_ptr(), table.numel(),
+                check(L.icm_gc_quantize_index(view_bcp(y, B, C, P, Z * i), v_mu, v_sc, B, C, P, table.data_ptr(), table.numel(),
                                               gc._scale_bound_f, sym.data_ptr(), idx.data_ptr(), M * P, Z * P * i,
                                               v_hat, v_slot, NULL_VIEW, st), "icm_gc_quantize_index")
             elif mode == "forward":
                 v_lik = View(y_lik.data_ptr() + Z * i * P * 4, M * P, P, 1)
-                check(L.icm_gc_likelihood(view_bcp(y, B, Z, P, Z * i), v_mu, v_sc, B, Z, P, gc._scale_bound_f,
+                check(L.icm_gc_likelihood(view_bcp(y, B, C, P, Z * i), v_mu, v_sc, B, C, P, gc._scale_bound_f,
                                           gc.likelihood_bound if gc.use_likelihood_bound else 0.0, v_hat, v_lik, v_slot, NULL_VIEW, st),
                       "icm_gc_likelihood")
             else:
-                check(L.icm_gc_build_indexes(v_sc, B, Z, P, table.data_ptr(), table.numel(), gc._scale_bound_f,
-                                             idx_s.data_ptr(), Z * P, 0, st), "icm_gc_build_indexes")
+                idx_s = torch.empty((B, C * P), dtype=torch.int32, device=dev)
+                sym_s = torch.empty_like(idx_s)
+                check(L.icm_gc_build_indexes(v_sc, B, C, P, table.data_ptr(), table.numel(), gc._scale_bound_f,
+                                             idx_s.data_ptr(), C * P, 0, st), "icm_gc_build_indexes")
                 decoder.decode_step(gct, idx_s, out=sym_s)
-                check(L.icm_gc_dequantize(sym_s.data_ptr(), Z * P, 0, v_mu, B, Z, P, v_hat, v_slot, NULL_VIEW, st), "icm_gc_dequantize")
-            lrp, _, _ = e.conv_stack(mean_sup, B, h, w, self.lrp_transforms[i], final_act=ACT_HALF_TANH)
-            keep = i < self.max_support_slices  # only the first max_support_slices decoded slices are ever used as support (stf.py:612, cnn.py:162)
-            check(L.icm_add_lrp(v_hat, view_bcp(lrp, B, Z, P), B, Z, P,
-                                v_slot if keep else NULL_VIEW, view_bcp(scale_sup, B, Z, P, M + Z * i) if keep else NULL_VIEW, st),
+                check(L.icm_gc_dequantize(sym_s.data_ptr(), C * P, 0, v_mu, B, C, P, v_hat, v_slot, NULL_VIEW, st), "icm_gc_dequantize")
+            if n > 1:
+                lrp = torch.empty((B * P, C), dtype=torch.float32, device=dev)
+                e.conv_stack_group(mean_sup, B, h, w, list(self.lrp_transforms[i:]), B, [0] * n, tail_channels=[M + Z * (i + g) for g in range(n)],
+                                   final_act=ACT_HALF_TANH, final_out=lrp, final_out_group_stride=Z, cin=M + Z * (k + 1))
+            else:
+                tc = [M + Z * i] if (tail and i >= S) else None
+                if tc is not None:
+                    lrp, _, _ = e.conv_stack_group(mean_sup, B, h, w, [self.lrp_transforms[i]], B, [0], tail_channels=tc,
+                                                   final_act=ACT_HALF_TANH, cin=M + Z * (k + 1))
+                    lrp = lrp[0]
+                else:
+                    lrp, _, _ = e.conv_stack(mean_sup, B, h, w, self.lrp_transforms[i], final_act=ACT_HALF_TANH, cin=M + Z * (k + 1))
+            keep = i < S and n == 1  # only the first max_support_slices decoded slices are ever used as support (stf.py:612, cnn.py:162)
+            check(L.icm_add_lrp(v_hat, view_bcp(lrp, B, C, P), B, C, P,
+                                v_slot if keep else NULL_VIEW, view_bcp(scale_sup, B, C, P, M + Z * i) if keep else NULL_VIEW, st),
                   "icm_add_lrp")
         return y_hat, sym, idx
 

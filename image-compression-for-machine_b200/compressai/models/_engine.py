@@ -10,7 +10,7 @@ import torch
 
 from compressai import _native
 from compressai._native import (ACT_GELU, ACT_NONE, ACT_RSQRT, ACT_SIGMOID, ACT_SQRT, OUT_BF16, OUT_F32, RES_ADD, RES_ADD_BEFORE_ACT,
-                                RES_MUL, ConvArgs, NativeError, check, lib, stream_ptr)
+                                RES_MUL, ConvArgs, ConvGroups, NativeError, check, lib, stream_ptr)
 
 
 class PackedConv:
@@ -59,6 +59,22 @@ class PackedDeconv:
         self.bias = b.reshape(-1).contiguous()
 
 
+class PackedGroup:
+    """The packed weights of G same-shaped layers stacked [G * Cout_pad, K] (+ biases [G, Cout]) for icm_conv2d_grouped."""
+
+    __slots__ = ("w", "bias", "Cin", "Cout", "KH", "KW", "stride", "pad", "ps", "G", "rows")
+
+    def __init__(self, pks):
+        p0 = pks[0]
+        for pk in pks:
+            assert (pk.Cin, pk.Cout, pk.KH, pk.KW, pk.stride, pk.pad, pk.ps) == (p0.Cin, p0.Cout, p0.KH, p0.KW, p0.stride, p0.pad, p0.ps)
+            assert (pk.bias is None) == (p0.bias is None)
+        self.Cin, self.Cout, self.KH, self.KW, self.stride, self.pad, self.ps = p0.Cin, p0.Cout, p0.KH, p0.KW, p0.stride, p0.pad, p0.ps
+        self.G, self.rows = len(pks), p0.w.shape[0]
+        self.w = torch.cat([pk.w for pk in pks], 0).contiguous()
+        self.bias = torch.stack([pk.bias for pk in pks], 0).contiguous() if p0.bias is not None else None
+
+
 class Engine:
     def __init__(self, model):
         self.model = model
@@ -95,6 +111,18 @@ class Engine:
             self._packed[key] = (pk, module, self._versions(module))  # holding the module keeps its id() from being reused
             torch.cuda.current_stream().synchronize()  # packed before any other stream may use it (micro-batches)
         return pk
+
+    def packed_group(self, modules, ps=0):
+        """Stacked packed weights of same-shaped layers (one icm_conv2d_grouped launch)."""
+        key = (tuple(id(m) for m in modules), ps, "group")
+        vers = tuple(self._versions(m) for m in modules)
+        hit = self._packed.get(key)
+        if hit is not None and hit[2] == vers:
+            return hit[0]
+        pg = PackedGroup([self.packed(m, ps) for m in modules])
+        self._packed[key] = (pg, tuple(modules), vers)
+        torch.cuda.current_stream().synchronize()
+        return pg
 
     def f32(self, p):
         key = (id(p), "f32")
@@ -134,6 +162,71 @@ class Engine:
         a.res_mode = res_mode
         check(lib().icm_conv2d(C.byref(a), stream_ptr()), "icm_conv2d")
         return out
+
+    def conv_group(self, x, B, H, W, pg, in_images, in_offsets, tail_channels=None, out=None, out_offset=0, out_group_stride=None,
+                   act=ACT_NONE, out_dtype=OUT_BF16, cin=None):
+        """G same-shaped convolutions in one launch (icm_conv2d_grouped).  x: bf16 channels-last tensor of `in_images` images;
+        group g reads images [in_offsets[g], +B).  Output: stacked [G, B*Ho*Wo(*r*r), Cout(/r^2)] unless `out` is given, then group g
+        writes at element offset out_offset + g * out_group_stride of it (row pitch = out.shape[-1])."""
+        assert x.dtype == torch.bfloat16 and x.is_cuda
+        cin = pg.Cin if cin is None else cin
+        if cin != pg.Cin:
+            raise NativeError(f"conv_group: input channels {cin} != weight channels {pg.Cin}")
+        Ho = (H + 2 * pg.pad - pg.KH) // pg.stride + 1
+        Wo = (W + 2 * pg.pad - pg.KW) // pg.stride + 1
+        r = pg.ps if pg.ps else 1
+        cout_eff = pg.Cout // (r * r)
+        G = pg.G
+        if out is None:
+            out = torch.empty((G, B * Ho * r * Wo * r, cout_eff), dtype=torch.float32 if out_dtype == OUT_F32 else torch.bfloat16, device=x.device)
+            out_group_stride = out.shape[1] * out.shape[2]
+        a = ConvArgs()
+        a.inp, a.weight = x.data_ptr(), pg.w.data_ptr()
+        a.bias = pg.bias.data_ptr() if pg.bias is not None else None
+        a.out = out.data_ptr() + out_offset * out.element_size()
+        a.residual = None
+        a.B, a.H, a.W, a.Cin, a.in_pitch = B, H, W, cin, x.shape[-1]
+        a.Cout, a.out_pitch = pg.Cout, out.shape[-1]
+        a.KH, a.KW, a.stride, a.pad = pg.KH, pg.KW, pg.stride, pg.pad
+        a.act, a.out_dtype, a.pixel_shuffle = act, out_dtype, pg.ps
+        a.res_pitch, a.res_dtype, a.res_mode = 0, OUT_F32, 0
+        g = ConvGroups()
+        g.groups, g.in_images = G, in_images
+        g.weight_group_rows = pg.rows
+        g.bias_group_stride = pg.bias.shape[1] if pg.bias is not None else 0
+        g.out_group_stride = out_group_stride
+        for k in range(G):
+            g.in_image_offset[k] = in_offsets[k]
+            g.tail_channel[k] = tail_channels[k] if tail_channels is not None else -1
+        check(lib().icm_conv2d_grouped(C.byref(a), C.byref(g), stream_ptr()), "icm_conv2d_grouped")
+        return out
+
+    def conv_stack_group(self, x, B, H, W, seqs, in_images, in_offsets, tail_channels=None, final_dtype=OUT_F32, final_act=ACT_NONE,
+                         final_out=None, final_out_offset=0, final_out_group_stride=None, cin=None):
+        """G same-shaped nn.Sequential conv stacks, layer by layer in grouped launches; the intermediate activations are
+        stacked [G*B, H, W, C]."""
+        per = [[(m, 0) if isinstance(m, torch.nn.Conv2d) else (m[0], m[1].upscale_factor)
+                for m in seq if isinstance(m, (torch.nn.Conv2d, torch.nn.Sequential))] for seq in seqs]
+        G, n = len(seqs), len(per[0])
+        for k in range(n):
+            last = k == n - 1
+            ps = per[0][k][1]
+            pg = self.packed_group([per[g][k][0] for g in range(G)], ps)
+            kw = dict(cin=cin) if k == 0 else {}
+            if k == 0:
+                ii, io, tc = in_images, in_offsets, tail_channels
+            else:
+                ii, io, tc = G * B, [g * B for g in range(G)], None
+            if last:
+                x = self.conv_group(x, B, H, W, pg, ii, io, tc, out=final_out, out_offset=final_out_offset,
+                                    out_group_stride=final_out_group_stride, act=final_act, out_dtype=final_dtype, **kw)
+            else:
+                x = self.conv_group(x, B, H, W, pg, ii, io, tc, act=ACT_GELU, **kw)
+            H = (H + 2 * pg.pad - pg.KH) // pg.stride + 1
+            W = (W + 2 * pg.pad - pg.KW) // pg.stride + 1
+            if ps:
+                H, W = H * ps, W * ps
+        return x, H, W
 
     def linear(self, x, pk, **kw):
         """x: bf16 [M, K] -> [M, N]."""

@@ -43,6 +43,15 @@ struct ConvParams {
     const void *residual;
     void *out;
     int *sched;              // {next tile to hand out beyond the first wave, CTAs finished}: this stream's tile counter
+    // grouped launch (icm_conv2d_grouped): G convolutions of one geometry, tile id = g * tiles_per_group + tile in group
+    int groups, tiles_per_group;
+    unsigned long long fd_g;
+    int w_group_rows;            // packed-weight rows between groups
+    int bias_group_stride;       // floats between the groups' biases in global memory
+    long long out_group_stride;  // output elements between groups
+    int has_tail;                // the last 64-channel chunk of a tap is read at tail_ch[g]
+    int a_img[ICM_MAX_CONV_GROUPS];   // first image of group g in the input tensor
+    int tail_ch[ICM_MAX_CONV_GROUPS];
 };
 
 // The activation switch sits OUTSIDE the 16-element loop (one uniform branch per chunk): with it inside, the
@@ -118,7 +127,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int a = 0; a < TQ; ++a) { mbar_init(&tq_full[a], 1); mbar_init(&tq_empty[a], EPI_WARPS + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += blockDim.x) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    {
+        const int per_group = p.n_tiles * p.BN;
+        for (int i = threadIdx.x; i < p.groups * per_group; i += blockDim.x) {
+            const int g = i / per_group, j = i - g * per_group;
+            s_bias[i] = (p.bias && j < p.Cout) ? p.bias[(long long)g * p.bias_group_stride + j] : 0.f;
+        }
+    }
     if (warp == 1) { // TMEM allocation is warp-collective
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -131,8 +146,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // tile id -> (n tile fastest, then w, h, image)
     // (three runtime integer divisions cost ~100 instructions per tile: 10 % of the epilogue of a K = 48 linear)
     auto fdiv = [](uint32_t n, unsigned long long m) -> uint32_t { return m ? (uint32_t)(((unsigned long long)n * m) >> 40) : n; };
-    auto tile_coords = [&](int tile, int &n0, int &w0, int &h0, int &b) {
-        uint32_t t = (uint32_t)tile, q = fdiv(t, p.fd_n);
+    auto tile_coords = [&](int tile, int &n0, int &w0, int &h0, int &b, int &g) {
+        uint32_t t = (uint32_t)tile, q = fdiv(t, p.fd_g);
+        if (p.groups > 1) { g = (int)q; t -= q * (uint32_t)p.tiles_per_group; } else g = 0;
+        q = fdiv(t, p.fd_n);
         const int nt = (int)(t - q * (uint32_t)p.n_tiles); t = q;
         q = fdiv(t, p.fd_w);
         const int tw_i = (int)(t - q * (uint32_t)p.tiles_w); t = q;
@@ -158,9 +175,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++slot == TQ) { slot = 0; qphase ^= 1; }
                 if (tile >= p.total_tiles) break;
                 const int next = (int)gridDim.x + atomicAdd(p.sched, 1); // in flight while this tile's loads are issued
-                int n0, w0, h0, b;
-                tile_coords(tile, n0, w0, h0, b);
+                int n0, w0, h0, b, g;
+                tile_coords(tile, n0, w0, h0, b, g);
                 tile = next;
+                const int img = b + p.a_img[g], wrow = n0 + g * p.w_group_rows;
+                const int tail_c = p.has_tail ? p.tail_ch[g] : (p.k_chunks - 1) * BK;
                 for (int it = 0; it < k_iters; ++it) {
                     const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
                     const int dy = tap / p.KW, dx = tap - dy * p.KW;
@@ -168,8 +187,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     unsigned char *sa = tiles + (size_t)stage * stage_bytes;
                     unsigned char *sb = sa + a_bytes;
                     mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-                    tma_load_4d(&map_a, &full_bar[stage], sa, chunk * BK, w0 * p.stride + dx - p.pad, h0 * p.stride + dy - p.pad, b);
-                    tma_load_2d(&map_w, &full_bar[stage], sb, tap * p.Cin_pad + chunk * BK, n0);
+                    tma_load_4d(&map_a, &full_bar[stage], sa, chunk == p.k_chunks - 1 ? tail_c : chunk * BK, w0 * p.stride + dx - p.pad,
+                                h0 * p.stride + dy - p.pad, img);
+                    tma_load_2d(&map_w, &full_bar[stage], sb, tap * p.Cin_pad + chunk * BK, wrow);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -234,11 +254,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         // one 16-column chunk: bias, second operand, activation, store
-        auto finish = [&](uint32_t (&accv)[16], int n, bool valid, long long pix, int b, int oh, int ow) {
+        auto finish = [&](uint32_t (&accv)[16], int n, bool valid, long long pix, int b, int oh, int ow, int g) {
             if (!valid || n >= p.Cout) return;
             float v[16];
             {
-                const float4 *bp = reinterpret_cast<const float4 *>(s_bias + n);
+                const float4 *bp = reinterpret_cast<const float4 *>(s_bias + g * (p.n_tiles * p.BN) + n);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 t = bp[j];
@@ -297,6 +317,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 off = pix * p.out_pitch + n;
             }
             if (p.residual && p.res_mode != 1) combine(p.res_mode);
+            off += (long long)g * p.out_group_stride;
             // 32-byte stores (st.global.v8, sm_100): one full sector per lane and instruction instead of two half-sector writes
             if (p.out_dtype == ICM_OUT_F32) {
                 float *op = reinterpret_cast<float *>(p.out) + off;
@@ -335,8 +356,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (lane == 0) mbar_arrive(&tq_empty[slot]);
             if (++slot == TQ) { slot = 0; qphase ^= 1; }
             if (tile < 0) break;
-            int n0, w0, h0, b;
-            tile_coords(tile, n0, w0, h0, b);
+            int n0, w0, h0, b, g;
+            tile_coords(tile, n0, w0, h0, b, g);
             const int oh = h0 + th, ow = w0 + tw;
             const bool valid = (oh < p.Ho) && (ow < p.Wo);
             const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
@@ -359,12 +380,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             while (c16 < n_chunks) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (c16 + 4 < n_chunks) tmem_ld16(tmem_d + (uint32_t)((c16 + 4) * 16), rb); else release();
-                finish(ra, n0 + c16 * 16, valid, pix, b, oh, ow);
+                finish(ra, n0 + c16 * 16, valid, pix, b, oh, ow, g);
                 c16 += 4;
                 if (c16 >= n_chunks) break;
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (c16 + 4 < n_chunks) tmem_ld16(tmem_d + (uint32_t)((c16 + 4) * 16), ra); else release();
-                finish(rb, n0 + c16 * 16, valid, pix, b, oh, ow);
+                finish(rb, n0 + c16 * 16, valid, pix, b, oh, ow, g);
                 c16 += 4;
             }
             if (!released) release(); // a warp with no chunk of this tile
@@ -464,9 +485,12 @@ extern "C" int icm_set_conv_sm_limit(int n_sms)
     return ICM_OK;
 }
 
-extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
+static int launch_conv(const icm_conv_args *a, const icm_conv_groups *grp, void *stream)
 {
     ICM_CHECK_ARG(a && a->in && a->weight && a->out, "icm_conv2d: null argument");
+    const int G = grp ? grp->groups : 1;
+    ICM_CHECK_ARG(G >= 1 && G <= ICM_MAX_CONV_GROUPS, "icm_conv2d_grouped: groups=%d outside 1..%d", G, ICM_MAX_CONV_GROUPS);
+    ICM_CHECK_ARG(G == 1 || a->residual == nullptr, "icm_conv2d_grouped: a residual operand needs groups == 1");
     ICM_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "icm_conv2d: empty input");
     ICM_CHECK_ARG(a->Cin > 0 && a->Cin <= a->in_pitch && a->in_pitch % 8 == 0, "icm_conv2d: Cin=%d in_pitch=%d (pitch must be a multiple of 8 and >= Cin)", a->Cin, a->in_pitch);
     ICM_CHECK_ARG(a->Cout > 0 && a->Cout % 16 == 0, "icm_conv2d: Cout=%d must be a multiple of 16", a->Cout);
@@ -496,7 +520,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.BN = ((a->Cout + n_tiles - 1) / n_tiles + 15) & ~15;
     // small problems: more, narrower N tiles so that more SMs take part
     const long long m_tiles = (long long)a->B * p.tiles_w * p.tiles_h;
-    while (p.BN > 64 && p.BN % 32 == 0 && m_tiles * ((a->Cout + p.BN - 1) / p.BN) * 2 <= sm_count()) p.BN /= 2;
+    while (p.BN > 64 && p.BN % 32 == 0 && G * m_tiles * ((a->Cout + p.BN - 1) / p.BN) * 2 <= sm_count()) p.BN /= 2;
     p.tmem_cols = 64;
     while (p.tmem_cols < 2 * p.BN) p.tmem_cols *= 2; // two accumulators, power-of-two allocation, <= 512
     const int k_iters = p.KH * p.KW * p.k_chunks;
@@ -510,6 +534,28 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     p.out_pitch = a->out_pitch; p.res_pitch = a->res_pitch;
     p.bias = a->bias; p.residual = a->residual; p.out = a->out;
     p.res_dtype = a->res_dtype; p.res_mode = a->res_mode;
+    p.groups = G;
+    int in_images = a->B;
+    if (grp) {
+        ICM_CHECK_ARG(grp->weight_group_rows >= ((a->Cout + 15) & ~15) || G == 1, "icm_conv2d_grouped: weight_group_rows smaller than the padded Cout");
+        ICM_CHECK_ARG(grp->in_images >= a->B, "icm_conv2d_grouped: in_images < B");
+        p.w_group_rows = (int)grp->weight_group_rows;
+        p.bias_group_stride = (int)grp->bias_group_stride;
+        p.out_group_stride = grp->out_group_stride;
+        in_images = grp->in_images;
+        for (int g = 0; g < G; ++g) {
+            ICM_CHECK_ARG(grp->in_image_offset[g] >= 0 && grp->in_image_offset[g] + a->B <= grp->in_images, "icm_conv2d_grouped: group %d reads images outside the input", g);
+            p.a_img[g] = grp->in_image_offset[g];
+            p.tail_ch[g] = grp->tail_channel[g];
+            if (grp->tail_channel[g] >= 0) p.has_tail = 1;
+        }
+        if (p.has_tail) {
+            const int tail = Cin - (p.k_chunks - 1) * BK; // channels of the tail chunk
+            for (int g = 0; g < G; ++g)
+                ICM_CHECK_ARG(grp->tail_channel[g] >= 0 && grp->tail_channel[g] % 8 == 0 && grp->tail_channel[g] + tail <= a->in_pitch,
+                              "icm_conv2d_grouped: tail_channel[%d]=%d (need every group set, 16-byte aligned, inside the row)", g, grp->tail_channel[g]);
+        }
+    }
     {
         const long long es = a->out_dtype == ICM_OUT_F32 ? 4 : 2;
         const int cq = ps ? a->Cout / (ps * ps) : 16;
@@ -524,7 +570,8 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
 
     CUtensorMap map_a, map_w;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        // a tail chunk is read at a channel of its own (up to the row pitch); otherwise channels beyond Cin are zero-filled
+        cuuint64_t dims[4] = {(cuuint64_t)(p.has_tail ? a->in_pitch : Cin), (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)in_images};
         cuuint64_t strides[3] = {(cuuint64_t)a->in_pitch * 2, (cuuint64_t)a->W * a->in_pitch * 2, (cuuint64_t)a->H * a->W * a->in_pitch * 2};
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)((TW - 1) * a->stride + 1), (cuuint32_t)((TH - 1) * a->stride + 1), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)a->stride, (cuuint32_t)a->stride, 1};
@@ -536,7 +583,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     {
         const cuuint64_t ktot = (cuuint64_t)p.KH * p.KW * p.Cin_pad;
         const int cout_pad = (a->Cout + 15) & ~15;
-        cuuint64_t dims[2] = {ktot, (cuuint64_t)cout_pad};
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)(G > 1 ? (long long)(G - 1) * p.w_group_rows + cout_pad : cout_pad)};
         cuuint64_t strides[1] = {ktot * 2};
         cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)p.BN};
         cuuint32_t estr[2] = {1, 1};
@@ -546,7 +593,7 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
         if (r != CUDA_SUCCESS) { set_error("icm_conv2d: cuTensorMapEncodeTiled(W) failed (%d)", (int)r); return ICM_ERR_CUDA; }
     }
     p.n_tiles = (a->Cout + p.BN - 1) / p.BN;
-    const size_t bias_bytes = (size_t)p.n_tiles * p.BN * 4;
+    const size_t bias_bytes = (size_t)G * p.n_tiles * p.BN * 4;
     ICM_CHECK_ARG(bias_bytes <= 16 * 1024, "icm_conv2d: Cout=%d too wide for the bias staging area", a->Cout);
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 4 + 2 * TQ) * 8 + TQ * 4 + 16 + bias_bytes;
     static PerDeviceSmem configured;
@@ -554,10 +601,12 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
         ICM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured.done(227 * 1024);
     }
-    ICM_CHECK_ARG(m_tiles * p.n_tiles < (1 << 24) && p.tiles_w < 65536 && p.tiles_h < 65536, "icm_conv2d: too many tiles");
-    p.total_tiles = (int)(m_tiles * p.n_tiles);
+    ICM_CHECK_ARG(G * m_tiles * p.n_tiles < (1 << 24) && p.tiles_w < 65536 && p.tiles_h < 65536, "icm_conv2d: too many tiles");
+    p.tiles_per_group = (int)(m_tiles * p.n_tiles);
+    p.total_tiles = G * p.tiles_per_group;
     auto magic = [](int d) -> unsigned long long { return d <= 1 ? 0ull : ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; };
     p.fd_n = magic(p.n_tiles); p.fd_w = magic(p.tiles_w); p.fd_h = magic(p.tiles_h);
+    p.fd_g = G > 1 ? magic(p.tiles_per_group) : 0;
     p.sched = tile_counter(as_stream(stream));
     if (!p.sched) return ICM_ERR_CUDA;
     const int max_ctas = persistent_grid_limit();
@@ -565,6 +614,14 @@ extern "C" int icm_conv2d(const icm_conv_args *a, void *stream)
     conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
+}
+
+extern "C" int icm_conv2d(const icm_conv_args *a, void *stream) { return launch_conv(a, nullptr, stream); }
+
+extern "C" int icm_conv2d_grouped(const icm_conv_args *a, const icm_conv_groups *g, void *stream)
+{
+    ICM_CHECK_ARG(g, "icm_conv2d_grouped: null group description");
+    return launch_conv(a, g, stream);
 }
 
 extern "C" int icm_pack_conv_weight(const float *d_w_oihw, int Cout, int Cin, int KH, int KW, int Cin_pad, int Cout_pad,

@@ -179,6 +179,27 @@ typedef struct {
     int res_mode;          /* 0: out = act(acc) + res   1: out = act(acc + res)   2: out = act(acc) * res */
 } icm_conv_args;
 int icm_conv2d(const icm_conv_args *a, void *stream);
+/* G convolutions of ONE geometry (a) in one launch: the channel-conditional stacks of the context model are
+ * independent of each other wherever the reference's data flow allows it -- cc_mean_transforms[i] and
+ * cc_scale_transforms[i] of a slice (stf.py:613-620), and every stack of the slices i >= max_support_slices,
+ * whose support is the same first max_support_slices decoded slices (stf.py:612) -- so they share a launch
+ * instead of running as G small ones.  Group g uses rows [g*weight_group_rows, +Cout) of the stacked packed
+ * weight, bias + g*bias_group_stride, images [in_image_offset[g], +B) of `in` (a tensor of in_images images: 0 for
+ * a shared input, g*B for stacked ones) and writes at out + g*out_group_stride elements.  tail_channel[g] >= 0
+ * (then for every g): the last 64-channel chunk of each tap is read at that channel of `in` instead of at
+ * 64*(chunks-1) -- the LRP stacks read [support | y_hat_i] with a per-slice position of y_hat_i.  Per output element
+ * the reduction order equals icm_conv2d's, so the results are bit-identical to G separate calls. */
+#define ICM_MAX_CONV_GROUPS 16
+typedef struct {
+    int groups;
+    int in_images;
+    int64_t weight_group_rows;
+    int64_t bias_group_stride;   /* floats */
+    int64_t out_group_stride;    /* elements of the output type */
+    int in_image_offset[ICM_MAX_CONV_GROUPS];
+    int tail_channel[ICM_MAX_CONV_GROUPS];   /* -1: none */
+} icm_conv_groups;
+int icm_conv2d_grouped(const icm_conv_args *a, const icm_conv_groups *g, void *stream);
 /* Cap on the SMs icm_conv2d / icm_swin_mlp occupy (0 = all), for overlap with the rANS coders on another stream. */
 int icm_set_conv_sm_limit(int n_sms);
 /* Fused Swin MLP (stf.py:34-40 inside :194-198): x[row] += fc2(GELU(fc1(h[row]))), h = LayerNorm2(x) in bf16 [rows, C],

@@ -129,6 +129,30 @@ def test_micro_batched_streams_give_identical_results(model):
     assert torch.equal(d_dev["x_hat"], d_whole["x_hat"])
 
 
+def test_grouped_launches_do_not_change_a_byte(model):
+    """Grouped conv launches and the one-step coding of the slices >= max_support_slices (icm_conv2d_grouped,
+    models/_context.py) against the slice-by-slice loop of stf.py:611-631 / :754-776: strings, x_hat and likelihoods equal."""
+    from oracle import weights
+
+    xs = torch.cat([weights.seeded_image((1, 3, 128, 64), seed=30 + s) for s in range(3)]).cuda()
+    assert model.grouped and model._tail_grouped()
+    a = model.compress(xs)
+    da = model.decompress(a["strings"], a["shape"])
+    fa = model(xs)
+    model.grouped = False
+    try:
+        b = model.compress(xs)
+        db = model.decompress(b["strings"], b["shape"])
+        fb = model(xs)
+        mixed = model.decompress(a["strings"], a["shape"])  # encoder grouped, decoder not
+    finally:
+        model.grouped = True
+    assert a["strings"] == b["strings"]
+    assert torch.equal(da["x_hat"], db["x_hat"]) and torch.equal(mixed["x_hat"], da["x_hat"])
+    assert torch.equal(fa["x_hat"], fb["x_hat"])
+    assert torch.equal(fa["likelihoods"]["y"], fb["likelihoods"]["y"]) and torch.equal(fa["likelihoods"]["z"], fb["likelihoods"]["z"])
+
+
 def test_strings_decode_with_the_cpu_oracle(model, x):
     """Cross-implementation check: the GPU-produced y-string of an image decodes, with the pinned CPU coder
     and the GPU-side indexes, to the symbols the GPU encoder consumed."""

@@ -98,6 +98,46 @@ def test_conv_is_batch_invariant(eng):
     assert torch.equal(full[2 * 96:3 * 96], one)
 
 
+def _packed_group(pks):
+    from compressai.models._engine import PackedGroup
+
+    return PackedGroup(pks)
+
+
+def test_grouped_conv_is_bit_identical_to_separate_launches(eng):
+    """icm_conv2d_grouped: (a) G stacks reading ONE shared input, each with its own tail chunk ([support | y_hat_i] of the LRP
+    stacks of slices >= max_support, stf.py:623-626), (b) stacked inputs (layers 2..5 of grouped stacks, cc_mean || cc_scale),
+    (c) PixelShuffle outputs (h_mean_s || h_scale_s) -- every output element must equal the ungrouped kernel's bit for bit,
+    because encoder and decoder may mix the two forms."""
+    from compressai.models._engine import PackedConv
+
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 3, 8, 12
+    # (a) Cin = 128 support channels + 32 tail channels at per-group positions of a 320-wide row
+    G, pitch, Cs = 3, 320, 128
+    x = torch.randn(B * H * W, pitch, generator=g).cuda().bfloat16()
+    pks = [PackedConv((torch.randn(80, Cs + 32, 3, 3, generator=g) / 40).cuda(), torch.randn(80, generator=g).cuda(), 1, 1) for _ in range(G)]
+    tails = [Cs + 32 * (k + 1) for k in range(G)]
+    got = eng.conv_group(x, B, H, W, _packed_group(pks), B, [0] * G, tail_channels=tails, act=1, out_dtype=1)
+    for k in range(G):
+        xin = torch.cat([x[:, :Cs], x[:, tails[k]:tails[k] + 32]], 1).contiguous()
+        assert torch.equal(got[k], eng.conv(xin, B, H, W, pks[k], act=1, out_dtype=1)), f"shared input + tail, group {k}"
+    # (b) stacked inputs with image offsets, outputs interleaved into one wide row (mu / scale of several slices side by side)
+    xs = torch.randn(2 * B * H * W, 96, generator=g).cuda().bfloat16()
+    pk2 = [PackedConv((torch.randn(32, 96, 3, 3, generator=g) / 30).cuda(), torch.randn(32, generator=g).cuda(), 1, 1) for _ in range(2)]
+    wide = torch.zeros(B * H * W, 64, dtype=torch.float32, device="cuda")
+    eng.conv_group(xs, B, H, W, _packed_group(pk2), 2 * B, [0, B], out=wide, out_group_stride=32, act=2, out_dtype=1)
+    for k in range(2):
+        one = eng.conv(xs[k * B * H * W:(k + 1) * B * H * W].contiguous(), B, H, W, pk2[k], act=2, out_dtype=1)
+        assert torch.equal(wide[:, 32 * k:32 * k + 32], one), f"stacked input, group {k}"
+    # (c) PixelShuffle(2) outputs, shared input, bf16
+    xz = torch.randn(B * 3 * 4, 240, generator=g).cuda().bfloat16()
+    pk3 = [PackedConv((torch.randn(1152, 240, 3, 3, generator=g) / 45).cuda(), torch.randn(1152, generator=g).cuda(), 1, 1, 2) for _ in range(2)]
+    got = eng.conv_group(xz, B, 3, 4, _packed_group(pk3), B, [0, 0], act=1)
+    for k in range(2):
+        assert torch.equal(got[k], eng.conv(xz, B, 3, 4, pk3[k], act=1)), f"pixel shuffle, group {k}"
+
+
 @pytest.mark.parametrize("C,gather", [(48, False), (96, False), (384, False), (192, True), (768, True)])
 def test_layernorm(eng, C, gather):
     g = torch.Generator().manual_seed(C)
