@@ -35,6 +35,10 @@ class ConvArgs(C.Structure):
     ]
 
 
+class Rows(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stride", C.c_int64)]
+
+
 class ConvGroups(C.Structure):
     _fields_ = [("groups", C.c_int), ("in_images", C.c_int), ("weight_group_rows", C.c_int64), ("bias_group_stride", C.c_int64),
                 ("out_group_stride", C.c_int64), ("in_image_offset", C.c_int * 16), ("tail_channel", C.c_int * 16)]
@@ -172,6 +176,11 @@ def _load():
         "icm_eltwise_bf16": (I, [I, P, I64, P, I64, P, I64, P, I64, I64, I, P]),
         "icm_window_attention_wacnn": (I, [P, P, P, I, I, I, I, I, I, I, P]),
         "icm_pack_deconv_weight": (I, [P, I, I, I, I, P, P]),
+        "icm_gc_train_forward": (I, [Rows, Rows, Rows, Rows, I64, I64, F, F, Rows, Rows, P]),
+        "icm_gc_train_backward": (I, [Rows, Rows, Rows, Rows, Rows, Rows, I64, I64, F, F, Rows, Rows, Rows, P]),
+        "icm_grad_sumsq": (I, [P, I64, P, P]),
+        "icm_clip_coef": (I, [P, F, F, P, P, P]),
+        "icm_adam_step": (I, [P, P, P, P, I64, F, F, F, F, I, P, F, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library out of sync

@@ -171,11 +171,21 @@ class ChannelContextCodec(CompressionModel):
         return z, zh, zw
 
     # ---------------------------------------------------------------------------------- forward / codec
-    @torch.no_grad()
+    train_rng = None     # a compressai.models._train.TrainRng; None = draws on the device
+    train_fused = True   # fused Gaussian-stage kernels (csrc/train.cu) in the training-mode forward
+
     def forward(self, x):
-        """Eval-mode forward (stf.py:582-645): {"x_hat" (unclamped), "likelihoods": {"y", "z"}} in NCHW."""
+        """stf.py:582-645: {"x_hat" (unclamped), "likelihoods": {"y", "z"}} in NCHW.  Eval mode: the CUDA inference kernels,
+        no autograd.  Training mode (noise quantisation, DropPath, gradients): models/_train.py."""
         if self.training:
-            raise NativeError("training-mode forward (noise quantisation + autograd) is not part of the CUDA inference path; call .eval()")
+            return self._train_forward(x)
+        with torch.no_grad():
+            return self._eval_forward(x)
+
+    def _train_forward(self, x):
+        raise NativeError(f"{type(self).__name__}: the training-mode forward is built for the STF codec only (BASELINE.json configs[4]); call .eval()")
+
+    def _eval_forward(self, x):
         self._check_input(x)
         eb = self.entropy_bottleneck
         B = x.shape[0]

@@ -162,6 +162,11 @@ class SymmetricalTransFormer(ChannelContextCodec):
 
     scale_table_fn = staticmethod(get_scale_table)
 
+    def _train_forward(self, x):
+        from ._train import stf_train_forward
+
+        return stf_train_forward(self, x, rng=self.train_rng, fused=self.train_fused)
+
     # ---------------------------------------------------------------------------------- transforms
     def _analysis(self, x):
         """g_a (stf.py:584-595): image [B,3,H,W] -> y fp32 channels-last [B*h*w, 384]."""

@@ -276,6 +276,39 @@ int icm_window_attention_wacnn(const void *d_qkv, void *d_out, const float *d_bi
  * (models/utils.py:124-132). */
 int icm_pack_deconv_weight(const float *d_w_iohw, int Cin, int Cout, int Cin_pad, int Cq, void *d_out_bf16, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step (BASELINE.json configs[4]; reference train.py:172-214).  The transforms' backward
+ * runs through the host framework's autograd; these are the fused memory-bound pieces around it.
+ *
+ * icm_rows: a [rows, n] fp32 tensor whose rows are `stride` elements apart (a 32-channel slice of an NCHW latent:
+ * rows = B, n = 32*H*W, stride = C*H*W).
+ *
+ * icm_gc_train_forward: GaussianConditional.forward in training mode fused with the straight-through y_hat:
+ *     likelihood = max(Phi((.5 - v)/s) - Phi((-.5 - v)/s), likelihood_bound), v = |y + noise - mu|, s = max(scale, scale_bound)
+ *                  (entropy_models.py:126-135 "noise", :626-659; LowerBound bound_ops.py:21-62)
+ *     y_hat      = round(y - mu) + mu                                        (stf.py:622, ops.py:20-34)
+ * icm_gc_train_backward: gradients towards y, mu and scale given those of likelihood and y_hat, with LowerBound's
+ *     pass-through rule (x >= bound or grad < 0) for both bounds and the identity gradient of ste_round. */
+typedef struct {
+    void *ptr;
+    int64_t stride;
+} icm_rows;
+int icm_gc_train_forward(icm_rows y, icm_rows noise, icm_rows mu, icm_rows scale, int64_t rows, int64_t n, float scale_bound,
+                         float likelihood_bound, icm_rows likelihood, icm_rows y_hat, void *stream);
+int icm_gc_train_backward(icm_rows y, icm_rows noise, icm_rows mu, icm_rows scale, icm_rows g_likelihood, icm_rows g_y_hat,
+                          int64_t rows, int64_t n, float scale_bound, float likelihood_bound, icm_rows g_y, icm_rows g_mu,
+                          icm_rows g_scale, void *stream);
+/* torch.nn.utils.clip_grad_norm_ (train.py:208-209) on ONE flat fp32 gradient buffer, nothing read back by the host:
+ * *d_sumsq += sum(x^2) (zero it first; call once per buffer), then
+ * *d_coef = pre_scale * min(1, max_norm / (pre_scale * sqrt(*d_sumsq) + 1e-6))   (max_norm <= 0: no clipping),
+ * pre_scale = 1 / world when the buffer holds gradient SUMS over the data-parallel ranks; *d_norm (optional) = the norm. */
+int icm_grad_sumsq(const float *d_x, int64_t n, float *d_sumsq, void *stream);
+int icm_clip_coef(const float *d_sumsq, float max_norm, float pre_scale, float *d_coef, float *d_norm, void *stream);
+/* torch.optim.Adam.step (train.py:161-168, 210, 214) over flat buffers: g' = grad * grad_scale * (*d_grad_scale if given);
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps); t = step >= 1. */
+int icm_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, const float *d_grad_scale, float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

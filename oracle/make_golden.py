@@ -354,8 +354,70 @@ def eval_golden():
     refshim.uninstall(h)
 
 
+
+TRAIN_PROBES = ["h_a.8.bias", "cc_scale_transforms.3.8.bias", "cc_mean_transforms.0.0.bias", "lrp_transforms.11.8.bias",
+                "patch_embed.proj.bias", "layers.0.blocks.1.attn.relative_position_bias_table", "syn_layers.3.blocks.1.mlp.fc2.bias",
+                "layers.2.blocks.3.norm1.weight", "entropy_bottleneck._bias0", "entropy_bottleneck._matrix2", "entropy_bottleneck.quantiles",
+                "end_conv.2.bias"]
+
+
+def train_golden():
+    """One rate-distortion training step of the reference STF on the CPU (BASELINE.json configs[4] at a small size):
+    the UNMODIFIED reference modules in .train() (DropPath 0.2, noise quantisation; stf.py:582-645), the loss of
+    train.py:53-74 read with the model's "x_hat" key, clip_grad_norm_ 1.0, Adam 1e-5 on everything but the quantiles and
+    Adam 1e-4 on the quantiles after aux_loss.backward() (train.py:161-168, 196-214).  Records the loss terms, the total
+    gradient norm, the gradients of a few small parameters and those parameters after the step."""
+    import math
+
+    h = refshim.install("binary")
+    torch.manual_seed(0)
+    m = h["stf"].SymmetricalTransFormer()
+    m.load_state_dict(weights.seeded_state_dict(m.state_dict(), seed=0, stress=True))
+    m.train()
+    x = weights.seeded_image((2, 3, 128, 128), seed=41)
+    named = dict(m.named_parameters())
+    main = [p for n, p in named.items() if not n.endswith(".quantiles")]
+    aux = [p for n, p in named.items() if n.endswith(".quantiles")]
+    opt, aux_opt = torch.optim.Adam(main, lr=1e-5), torch.optim.Adam(aux, lr=1e-4)
+    lmbda = 800.0
+    out = {}
+    for step in range(2):
+        torch.manual_seed(4242 + step)
+        opt.zero_grad()
+        aux_opt.zero_grad()
+        o = m(x)
+        N, _, H, W = x.shape
+        bpp = sum(torch.log(l).sum() / (-math.log(2) * N * H * W) for l in o["likelihoods"].values())
+        mse = torch.nn.functional.mse_loss(x, o["x_hat"])
+        loss = lmbda * mse + bpp
+        loss.backward()
+        if step == 0:
+            for n in TRAIN_PROBES:
+                out["grad/" + n] = named[n].grad.detach().clone().numpy()
+                out["before/" + n] = named[n].detach().clone().numpy()
+        norm = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        a = m.aux_loss()
+        a.backward()
+        if step == 0:
+            out["aux_grad/entropy_bottleneck.quantiles"] = named["entropy_bottleneck.quantiles"].grad.detach().clone().numpy()
+        aux_opt.step()
+        out[f"loss{step}"], out[f"bpp{step}"], out[f"mse{step}"] = np.float64(loss.item()), np.float64(bpp.item()), np.float64(mse.item())
+        out[f"aux{step}"], out[f"norm{step}"] = np.float64(a.item()), np.float64(float(norm))
+        out[f"y_lik_logsum{step}"] = np.float64(torch.log(o["likelihoods"]["y"]).sum().item())
+        out[f"z_lik_logsum{step}"] = np.float64(torch.log(o["likelihoods"]["z"]).sum().item())
+        if step == 0:
+            for n in TRAIN_PROBES:
+                out["after/" + n] = named[n].detach().clone().numpy()
+        print(f"train step {step}: loss {loss.item():.6f} bpp {bpp.item():.6f} mse {mse.item():.6f} aux {a.item():.4f} |g| {float(norm):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "train_step.npz"), **out)
+    refshim.uninstall(h)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["eval"]:
+    if sys.argv[1:] == ["train"]:
+        train_golden()
+    elif sys.argv[1:] == ["eval"]:
         eval_golden()
     elif sys.argv[1:] == ["stf_full"]:
         stf_full_golden()
@@ -369,3 +431,4 @@ if __name__ == "__main__":
         cnn2_full_golden()
         stf_full_golden()
         eval_golden()
+        train_golden()
