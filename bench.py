@@ -168,6 +168,64 @@ def cpu_baseline(model_sd, n_images, steps=1, warmup=0):
     return n_images / dt, dt
 
 
+def train_bench(dev, rank, world, dist, steps=6, warmup=3, total_batch=16, size=256):
+    """BASELINE.json configs[4]: one rate-distortion training step of STF on `total_batch` 3 x size x size crops, sharded over
+    the ranks (strong scaling: 16 / N per GPU), Adam 1e-5 / 1e-4, clip 1.0, gradient all-reduce over NCCL in buckets that
+    overlap backward (compressai/training.py).  Transforms forward/backward: PyTorch autograd (library GEMMs/convolutions);
+    Gaussian stage, clipping and both Adams: csrc/train.cu.  Timed with CUDA events, max over ranks."""
+    from compressai.training import Trainer
+    from compressai.zoo import models
+    from compressai.utils.sharding import max_over_ranks
+
+    per = max(1, total_batch // world)
+    out = {"workload": f"stf training step, {total_batch}x3x{size}x{size} crops in total = {per} per GPU (BASELINE.json configs[4]), "
+                       f"RateDistortionLoss lambda 800, Adam 1e-5 + aux Adam 1e-4, clip_grad_norm 1.0", "n_gpus": world, "steps": steps, "warmup": warmup}
+    for label, autocast in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        torch.manual_seed(0)
+        net = models["stf"]().to(dev).train()
+        tr = Trainer(net, lmbda=800.0, autocast=autocast)
+        g = torch.Generator().manual_seed(77 + rank)
+        x = torch.rand((per, 3, size, size), generator=g).pin_memory()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        loss = None
+        for it in range(warmup + steps):
+            if it == warmup:
+                if dist is not None:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0.record()
+            crit = tr.step(x.to(dev, non_blocking=True))   # host batch -> device inside the step
+            loss = crit["loss"]
+        e1.record()
+        loss_v = float(loss.item())                          # the step's result read back
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps if dist is not None else e0.elapsed_time(e1) / steps
+        # the flat Adam pass alone (28 B per parameter: p, g, m, v read; p, m, v written), against the HBM roofline
+        opt = tr.optimizer
+        ea.record()
+        for _ in range(5):
+            opt.step(1.0, 1.0 / world)
+        eb.record()
+        torch.cuda.synchronize()
+        adam_ms = ea.elapsed_time(eb) / 5
+        out[label] = {"ms_per_step": round(ms, 3), "images_per_s": round(total_batch / (ms / 1e3), 2), "loss_last": round(loss_v, 4),
+                      "adam_clip_ms": round(adam_ms, 4), "adam_clip_gb_s": round((28 + 4) * opt.n / (adam_ms / 1e3) / 1e9, 1)}
+        if label == "fp32":
+            out["parameters"] = int(opt.n + tr.aux_optimizer.n)
+            out["allreduce_bytes_per_step"] = int(4 * opt.n) if world > 1 else 0
+            out["gradient_buckets"] = len(tr.buckets.buckets)
+            out["precision"] = ("fp32 parameters / gradients / Adam state; fp32: PyTorch's default math modes like the reference's train.py "
+                                "(TF32 cuDNN convolutions, fp32 matmuls); bf16_autocast: transforms' GEMMs and convolutions in bf16, residual stream, "
+                                "entropy stage and loss in fp32")
+        tr.buckets.remove()
+        del tr, net
+        gc.collect()
+        torch.cuda.empty_cache()
+    out["timing"] = "CUDA events around K steps incl. the H2D copy of each batch shard, max over ranks; loss read back after the last step"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +246,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch images per GPU; strong: --batch images in total")
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-weights sub-record")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency sub-record")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE.json configs[4])")
     ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU arm / cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -371,6 +430,9 @@ def main():
                    "workload": "stf 1x3x768x512 compress + decompress (BASELINE.json configs[1]), plain API, host byte strings, one image at a time",
                    "timing": "wall clock incl. host enqueue and synchronisation, median of 7 after 2 warm-up runs"}
         del c1, d1
+    train = None
+    if not args.no_train and 16 % world == 0:
+        train = train_bench(dev, rank, world, dist)
     # instrumented step: per-entry-point CUDA events -> dominant kernel family and its roofline
     roofline, families = None, None
     if rank == 0:
@@ -428,7 +490,7 @@ def main():
             "dtype": "bf16 operands / fp32 accumulate (transforms); fp32 (entropy models); u64 (rANS)", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "stress": stress, "latency_b1": latency,
+            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "stress": stress, "latency_b1": latency, "train_step": train,
             "families": families,
             "msym_per_s": round(value * SYMBOLS_PER_IMAGE / 1e6, 2),
             "bytes_per_image": round(str_bytes / B, 1),

@@ -118,7 +118,13 @@ def test_training_step_matches_the_reference_step(gold):
     x = weights.seeded_image((2, 3, 128, 128), seed=41).cuda()
     grads = {}
     probes = [k[5:] for k in gold.files if k.startswith("grad/")]
-    hooks = [named[n].register_post_accumulate_grad_hook(lambda p, n=n: grads.setdefault(n, p.grad.detach().clone())) for n in probes]
+    def probe(n):
+        def hook(p):
+            if n not in grads:
+                grads[n] = p.grad.detach().clone()
+        return hook
+
+    hooks = [named[n].register_post_accumulate_grad_hook(probe(n)) for n in probes]
     for step in range(2):
         torch.manual_seed(4242 + step)
         crit = tr.step(x)
