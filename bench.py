@@ -180,10 +180,10 @@ def train_bench(dev, rank, world, dist, steps=6, warmup=3, total_batch=16, size=
     per = max(1, total_batch // world)
     out = {"workload": f"stf training step, {total_batch}x3x{size}x{size} crops in total = {per} per GPU (BASELINE.json configs[4]), "
                        f"RateDistortionLoss lambda 800, Adam 1e-5 + aux Adam 1e-4, clip_grad_norm 1.0", "n_gpus": world, "steps": steps, "warmup": warmup}
-    for label, autocast in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+    for label, autocast, graph in (("fp32", None, False), ("fp32_cuda_graph", None, True), ("bf16_autocast_cuda_graph", torch.bfloat16, True)):
         torch.manual_seed(0)
         net = models["stf"]().to(dev).train()
-        tr = Trainer(net, lmbda=800.0, autocast=autocast)
+        tr = Trainer(net, lmbda=800.0, autocast=autocast, cuda_graph=graph)
         g = torch.Generator().manual_seed(77 + rank)
         x = torch.rand((per, 3, size, size), generator=g).pin_memory()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,7 +200,7 @@ def train_bench(dev, rank, world, dist, steps=6, warmup=3, total_batch=16, size=
         e1.record()
         loss_v = float(loss.item())                          # the step's result read back
         torch.cuda.synchronize()
-        ms = max_over_ranks(e0.elapsed_time(e1)) / steps if dist is not None else e0.elapsed_time(e1) / steps
+        ms = max_over_ranks(e0.elapsed_time(e1), device=dev) / steps
         # the flat Adam pass alone (28 B per parameter: p, g, m, v read; p, m, v written), against the HBM roofline
         opt = tr.optimizer
         ea.record()
@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-weights sub-record")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency sub-record")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE.json configs[4])")
+    ap.add_argument("--train-only", action="store_true", help="print only the training-step record (development aid)")
     ap.add_argument("--cpu-images", type=int, default=2, help="images per step of the CPU arm / cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -312,6 +313,13 @@ def main():
     from compressai import _native
     from compressai.utils.sharding import max_over_ranks
 
+    if args.train_only:
+        rec = train_bench(dev, rank, world, dist, steps=args.steps, warmup=max(3, args.warmup))
+        if rank == 0:
+            print(json.dumps({"train_step": rec}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
     model = make_model(dev, args.weights)
     B = args.batch
     x_host = make_images(B, seed=rank).pin_memory()

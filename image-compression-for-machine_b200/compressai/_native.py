@@ -180,7 +180,7 @@ def _load():
         "icm_gc_train_backward": (I, [Rows, Rows, Rows, Rows, Rows, Rows, I64, I64, F, F, Rows, Rows, Rows, P]),
         "icm_grad_sumsq": (I, [P, I64, P, P]),
         "icm_clip_coef": (I, [P, F, F, P, P, P]),
-        "icm_adam_step": (I, [P, P, P, P, I64, F, F, F, F, I, P, F, P]),
+        "icm_adam_step": (I, [P, P, P, P, I64, F, F, F, F, I, P, P, F, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library out of sync

@@ -122,9 +122,21 @@ __global__ void clip_coef_kernel(const float *sumsq, float max_norm, float pre, 
     if (norm_out) *norm_out = norm;
 }
 
-__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
-                            float lr, float b1, float b2, float eps, float bc1, float rsqrt_bc2, const float *gscale_dev, float gscale)
+// Step counter and bias corrections kept on the device ({t, 1 - b1^t, 1 / sqrt(1 - b2^t)}), so that a training step captured in a
+// CUDA graph advances them on every replay.
+__global__ void adam_tick_kernel(float *state, float b1, float b2)
 {
+    const float t = state[0] + 1.f;
+    state[0] = t;
+    state[1] = (float)(1.0 - pow((double)b1, (double)t));
+    state[2] = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)t)));
+}
+
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
+                            float lr, float b1, float b2, float eps, float bc1, float rsqrt_bc2, const float *gscale_dev, float gscale,
+                            const float *state)
+{
+    if (state) { bc1 = state[1]; rsqrt_bc2 = state[2]; }
     const float gs = gscale_dev ? gscale * *gscale_dev : gscale;
     const float step = lr / bc1;
     const long long n4 = n >> 2;
@@ -217,17 +229,24 @@ extern "C" int icm_clip_coef(const float *d_sumsq, float max_norm, float pre_sca
 }
 
 extern "C" int icm_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr, float beta1,
-                             float beta2, float eps, int step, const float *d_grad_scale, float grad_scale, void *stream)
+                             float beta2, float eps, int step, float *d_step_state, const float *d_grad_scale, float grad_scale, void *stream)
 {
-    ICM_CHECK_ARG(d_param && d_grad && d_exp_avg && d_exp_avg_sq && n > 0 && step >= 1, "icm_adam_step: null argument or step < 1");
+    ICM_CHECK_ARG(d_param && d_grad && d_exp_avg && d_exp_avg_sq && n > 0 && (step >= 1 || d_step_state), "icm_adam_step: null argument or step < 1");
     ICM_CHECK_ARG((((uintptr_t)d_param | (uintptr_t)d_grad | (uintptr_t)d_exp_avg | (uintptr_t)d_exp_avg_sq) & 15) == 0, "icm_adam_step: buffers must be 16-byte aligned");
-    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    double bc1 = 1.0, bc2 = 1.0;
+    if (d_step_state) {
+        adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(d_step_state, beta1, beta2);
+        ICM_LAUNCH_CHECK();
+    } else {
+        bc1 = 1.0 - pow((double)beta1, step);
+        bc2 = 1.0 - pow((double)beta2, step);
+    }
     long long blocks = (n / 4 + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1,
-                                                                   (float)(1.0 / sqrt(bc2)), d_grad_scale, grad_scale);
+                                                                   (float)(1.0 / sqrt(bc2)), d_grad_scale, grad_scale, d_step_state);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }

@@ -305,9 +305,11 @@ int icm_gc_train_backward(icm_rows y, icm_rows noise, icm_rows mu, icm_rows scal
 int icm_grad_sumsq(const float *d_x, int64_t n, float *d_sumsq, void *stream);
 int icm_clip_coef(const float *d_sumsq, float max_norm, float pre_scale, float *d_coef, float *d_norm, void *stream);
 /* torch.optim.Adam.step (train.py:161-168, 210, 214) over flat buffers: g' = grad * grad_scale * (*d_grad_scale if given);
- * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps); t = step >= 1. */
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  t = step >= 1, or, with
+ * d_step_state (3 floats {t, 1-b1^t, 1/sqrt(1-b2^t)}, zero-initialised), a counter kept and advanced on the device, so that a
+ * step captured in a CUDA graph advances on every replay. */
 int icm_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr, float beta1,
-                  float beta2, float eps, int step, const float *d_grad_scale, float grad_scale, void *stream);
+                  float beta2, float eps, int step, float *d_step_state, const float *d_grad_scale, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }
