@@ -20,9 +20,10 @@ from compressai import _native  # noqa: E402
 
 
 def key_of(name, args):
-    if name == "icm_conv2d":
+    if name in ("icm_conv2d", "icm_conv2d_grouped"):
         a = args[0]._obj
-        return (name, a.B, a.H, a.W, a.Cin, a.Cout, a.KH, a.stride, a.act, a.out_dtype, a.pixel_shuffle, int(bool(a.residual)), a.res_mode)
+        G = args[1]._obj.groups if name == "icm_conv2d_grouped" else 1
+        return (name, a.B, a.H, a.W, a.Cin, a.Cout, a.KH, a.stride, a.act, a.out_dtype, a.pixel_shuffle, int(bool(a.residual)), a.res_mode, G)
     ints = tuple(int(v) for v in args if isinstance(v, int) and 0 <= v < (1 << 24))
     return (name,) + ints
 
