@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--decode-priority", type=int, default=-1, help="pipeline: run each job's decode loop on a high-priority stream (-1 = automatic)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch images per GPU; strong: --batch images in total")
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-weights sub-record")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record (64 images in total)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency sub-record")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE.json configs[4])")
     ap.add_argument("--train-only", action="store_true", help="print only the training-step record (development aid)")
@@ -257,13 +258,15 @@ def main():
     # Pipeline depth: the two coders are latency-bound (~35 ms + ~50 ms per job whatever its size), so throughput needs
     # ~400 images in flight; small per-GPU batches (strong scaling: 8 images per GPU at N = 8) therefore need more,
     # smaller jobs in flight.  The streams (and their high-priority twins) must fit the 32 hardware queues.
-    part_eff = max(1, min(args.part, b_gpu))
-    if args.streams < 0:
-        args.streams = max(12, min(32, -(-384 // part_eff)))
-    if args.decode_priority < 0:
-        args.decode_priority = 1 if args.streams <= 16 else 0
-    if args.lag < 0:
-        args.lag = 8 if args.streams <= 12 else args.streams - 3
+    def pipe_params(b):
+        part = max(1, min(args.part, b))
+        streams = args.streams if args.streams >= 0 else max(12, min(32, -(-384 // part)))
+        prio = args.decode_priority if args.decode_priority >= 0 else (1 if streams <= 16 else 0)
+        lag = args.lag if args.lag >= 0 else (8 if streams <= 12 else streams - 3)
+        return streams, part, lag, prio
+
+    auto = (args.streams, args.lag, args.decode_priority)
+    args.streams, _, args.lag, args.decode_priority = pipe_params(b_gpu)
     if args.scaling == "strong":
         if args.batch % world:
             raise SystemExit(f"--scaling strong: --batch {args.batch} is not a multiple of the {world} GPUs")
@@ -421,6 +424,27 @@ def main():
                   "weights": WEIGHTS["stress"], "y_bytes_per_image": round(nb2, 1), "timing": "as `value`: device-resident pipeline, CUDA events"}
         del m2, p2, c2
         torch.cuda.empty_cache()
+    # BASELINE configs[2] as written: the SAME 64 images sharded over the N GPUs (64 / N each), next to the weak-scaling
+    # headline (64 per GPU).  At N = 8 a GPU holds 8 images per step and the coders' latency needs many small jobs in flight.
+    strong = None
+    if world > 1 and args.scaling == "weak" and B % world == 0 and not args.no_strong:
+        bs = B // world
+        resolved = (args.streams, args.lag, args.decode_priority)
+        args.streams, args.lag, args.decode_priority = auto
+        st3, part3, lag3, prio3 = pipe_params(bs)
+        args.streams, args.lag, args.decode_priority = resolved
+        p3 = RoundTripPipeline(model, n_streams=st3, part=part3, conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
+                               decoder_streams_per_cta=args.dec_per_cta, lag=lag3, chains=args.chains, decode_priority=bool(prio3))
+        xs = x_dev[:bs].contiguous()
+        steps3 = args.steps * world  # the same number of images per GPU as the weak run
+        p3.roundtrip([xs] * max(3, -(-st3 // max(1, -(-bs // part3)))), keep_outputs=False)
+        torch.cuda.synchronize()
+        ms3, _, _ = timed(lambda k: p3.roundtrip([xs] * k, keep_outputs=False), steps3)
+        strong = {"value": round(B * steps3 / (ms3 / 1e3), 3), "unit": "images/s", "images_total_per_step": B, "images_per_gpu": bs,
+                  "steps": steps3, "ms_per_step": round(ms3 / steps3, 3), "scaling": "strong",
+                  "pipeline": f"{st3} streams x jobs of {part3} images, synthesis lagging {lag3} jobs", "timing": "as `value`"}
+        del p3, xs
+        torch.cuda.empty_cache()
     # BASELINE configs[1]: one image at a time through the plain API (host strings), median of 7
     latency = None
     if rank == 0 and not args.no_latency:
@@ -498,7 +522,7 @@ def main():
             "dtype": "bf16 operands / fp32 accumulate (transforms); fp32 (entropy models); u64 (rANS)", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "stress": stress, "latency_b1": latency, "train_step": train,
+            "gpu_launches": int(launches) * world, "roofline": roofline, "cpu_baseline": cpu, "stress": stress, "strong_scaling": strong, "latency_b1": latency, "train_step": train,
             "families": families,
             "msym_per_s": round(value * SYMBOLS_PER_IMAGE / 1e6, 2),
             "bytes_per_image": round(str_bytes / B, 1),

@@ -57,6 +57,8 @@ def main():
     for k in keys:
         entry = k["key"][0]
         n = len(owner.get(entry, [None]))
+        if entry == "icm_swin_block" and k["key"][4] == 96:
+            n = 2  # C = 96 runs the attention half and the MLP half as two kernels
         for j in range(n):
             if pi >= len(pending):
                 break
