@@ -240,7 +240,7 @@ def main():
     ap.add_argument("--part", type=int, default=32, help="images per pipeline job")
     ap.add_argument("--dec-per-cta", type=int, default=8, help="rANS decoder streams per CTA in the pipeline (1, 2, 4, 8, 16)")
     ap.add_argument("--lag", type=int, default=-1, help="pipeline: synthesis of job t is ordered after the compress transforms of job t+lag (-1 = automatic)")
-    ap.add_argument("--chains", type=int, default=2, help="pipeline: jobs allowed in a throughput-bound phase at once (0 = unordered)")
+    ap.add_argument("--chains", type=int, default=-1, help="pipeline: jobs allowed in a throughput-bound phase at once (0 = unordered; -1 = automatic: 2, or 4 for jobs of <= 8 images whose kernels do not fill the GPU)")
     ap.add_argument("--conv-sms", type=int, default=0, help="cap on SMs used by the conv kernel (0 = all: its tile scheduler is dynamic)")
     ap.add_argument("--decode-priority", type=int, default=-1, help="pipeline: run each job's decode loop on a high-priority stream (-1 = automatic)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch images per GPU; strong: --batch images in total")
@@ -265,8 +265,11 @@ def main():
         lag = args.lag if args.lag >= 0 else (8 if streams <= 12 else streams - 3)
         return streams, part, lag, prio
 
+    auto_chains = args.chains < 0
+    chains_for = lambda part: (4 if part <= 8 else 2) if auto_chains else args.chains
     auto = (args.streams, args.lag, args.decode_priority)
     args.streams, _, args.lag, args.decode_priority = pipe_params(b_gpu)
+    args.chains = chains_for(max(1, min(args.part, b_gpu)))
     if args.scaling == "strong":
         if args.batch % world:
             raise SystemExit(f"--scaling strong: --batch {args.batch} is not a multiple of the {world} GPUs")
@@ -434,7 +437,7 @@ def main():
         st3, part3, lag3, prio3 = pipe_params(bs)
         args.streams, args.lag, args.decode_priority = resolved
         p3 = RoundTripPipeline(model, n_streams=st3, part=part3, conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
-                               decoder_streams_per_cta=args.dec_per_cta, lag=lag3, chains=args.chains, decode_priority=bool(prio3))
+                               decoder_streams_per_cta=args.dec_per_cta, lag=lag3, chains=chains_for(part3), decode_priority=bool(prio3))
         xs = x_dev[:bs].contiguous()
         steps3 = args.steps * world  # the same number of images per GPU as the weak run
         p3.roundtrip([xs] * max(3, -(-st3 // max(1, -(-bs // part3)))), keep_outputs=False)
@@ -442,7 +445,7 @@ def main():
         ms3, _, _ = timed(lambda k: p3.roundtrip([xs] * k, keep_outputs=False), steps3)
         strong = {"value": round(B * steps3 / (ms3 / 1e3), 3), "unit": "images/s", "images_total_per_step": B, "images_per_gpu": bs,
                   "steps": steps3, "ms_per_step": round(ms3 / steps3, 3), "scaling": "strong",
-                  "pipeline": f"{st3} streams x jobs of {part3} images, synthesis lagging {lag3} jobs", "timing": "as `value`"}
+                  "pipeline": f"{st3} streams x jobs of {part3} images, {chains_for(part3)} event chains, synthesis lagging {lag3} jobs", "timing": "as `value`"}
         del p3, xs
         torch.cuda.empty_cache()
     # BASELINE configs[1]: one image at a time through the plain API (host strings), median of 7

@@ -198,7 +198,14 @@ def check(rc, what=""):
     return rc
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """The current CUDA stream as a void*.  Called once per kernel launch: the raw-stream query is ~10x cheaper than building a
+    torch.cuda.Stream object (it was 10 % of the host time of a pipelined step)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

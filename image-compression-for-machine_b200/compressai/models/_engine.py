@@ -90,7 +90,7 @@ class Engine:
     def _versions(module):
         """(data_ptr, _version) of every parameter of a holder: in-place edits (optimizer steps, weight.mul_) bump _version,
         re-assignment changes data_ptr -- either invalidates the packed copy, like EntropyBottleneck.packed_params()."""
-        return tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=False))
+        return tuple((p.data_ptr(), p._version) for p in module._parameters.values() if p is not None)
 
     def packed(self, module, ps=0):
         key = (id(module), ps)

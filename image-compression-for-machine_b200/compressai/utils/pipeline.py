@@ -69,8 +69,13 @@ class RoundTripPipeline:
         return self._decoders[key]
 
     def _pin(self, shape, dtype):
-        """A pinned staging buffer from the pool (returned by _unpin once its job's strings have been built)."""
-        free = self._pinned.setdefault((tuple(shape), dtype), [])
+        """A pinned staging buffer from the pool (returned by _unpin once its job's strings have been built).  The first request
+        for a shape allocates one buffer per job that can be in flight (cudaHostAlloc takes ~35 ms for a 40 MB buffer: it must
+        never happen in the middle of a run)."""
+        key = (tuple(shape), dtype)
+        free = self._pinned.get(key)
+        if free is None:
+            free = self._pinned[key] = [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(self.n_streams + 2)]
         return free.pop() if free else torch.empty(shape, dtype=dtype).pin_memory()
 
     def _unpin(self, *bufs):
