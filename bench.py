@@ -244,6 +244,7 @@ def main():
     ap.add_argument("--conv-sms", type=int, default=0, help="cap on SMs used by the conv kernel (0 = all: its tile scheduler is dynamic)")
     ap.add_argument("--decode-priority", type=int, default=-1, help="pipeline: run each job's decode loop on a high-priority stream (-1 = automatic)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch images per GPU; strong: --batch images in total")
+    ap.add_argument("--graphs", type=int, default=1, help="pipeline: replay each job from CUDA graphs captured per (stream slot, job shape)")
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-weights sub-record")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record (64 images in total)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-image latency sub-record")
@@ -336,7 +337,8 @@ def main():
 
     def make_pipe(mdl):
         return RoundTripPipeline(mdl, n_streams=args.streams, part=min(args.part, B), conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
-                                 decoder_streams_per_cta=args.dec_per_cta, lag=args.lag, chains=args.chains, decode_priority=bool(args.decode_priority))
+                                 decoder_streams_per_cta=args.dec_per_cta, lag=args.lag, chains=args.chains, decode_priority=bool(args.decode_priority),
+                                 cuda_graphs=bool(args.graphs))
 
     pipe = make_pipe(model)
     out_bufs = [out_host, torch.empty_like(out_host).pin_memory()] if not args.no_e2e else []
@@ -383,6 +385,8 @@ def main():
     # slice of the caching allocator and a decoder pair: their first use must not fall into the timed region)
     jobs_per_step = -(-B // min(args.part, B))
     warm_steps = max(args.warmup, 3, -(-args.streams // jobs_per_step))
+    if args.graphs:  # every stream slot runs one job eagerly, captures its graphs on the second, replays from the third
+        warm_steps = max(warm_steps, 2 * -(-args.streams // jobs_per_step) + 1)
     run_device(warm_steps)
     torch.cuda.synchronize()
     # the device-resident pipeline (no per-job host read) must give exactly what the host-string API gives
@@ -437,10 +441,11 @@ def main():
         st3, part3, lag3, prio3 = pipe_params(bs)
         args.streams, args.lag, args.decode_priority = resolved
         p3 = RoundTripPipeline(model, n_streams=st3, part=part3, conv_sm_limit=(args.conv_sms if args.conv_sms >= 0 else None),
-                               decoder_streams_per_cta=args.dec_per_cta, lag=lag3, chains=chains_for(part3), decode_priority=bool(prio3))
+                               decoder_streams_per_cta=args.dec_per_cta, lag=lag3, chains=chains_for(part3), decode_priority=bool(prio3),
+                               cuda_graphs=bool(args.graphs))
         xs = x_dev[:bs].contiguous()
         steps3 = args.steps * world  # the same number of images per GPU as the weak run
-        p3.roundtrip([xs] * max(3, -(-st3 // max(1, -(-bs // part3)))), keep_outputs=False)
+        p3.roundtrip([xs] * max(3, (2 if args.graphs else 1) * -(-st3 // max(1, -(-bs // part3))) + 1), keep_outputs=False)
         torch.cuda.synchronize()
         ms3, _, _ = timed(lambda k: p3.roundtrip([xs] * k, keep_outputs=False), steps3)
         strong = {"value": round(B * steps3 / (ms3 / 1e3), 3), "unit": "images/s", "images_total_per_step": B, "images_per_gpu": bs,

@@ -52,7 +52,7 @@ class Profile:
     """Wraps every device entry point with a CUDA-event pair on the current stream (bench.py's roofline
     pass).  Usage: `with Profile() as p: model.compress(x)`; `p.summary()` -> {entry: (calls, ms, work)}."""
 
-    _HOST = {"icm_last_error", "icm_abi_version", "icm_launch_count", "icm_pmf_to_quantized_cdf", "icm_tables_create",
+    _HOST = {"icm_last_error", "icm_abi_version", "icm_launch_count", "icm_note_graph_launches", "icm_pmf_to_quantized_cdf", "icm_tables_create",
              "icm_tables_destroy", "icm_rans_encode_workspace_bytes", "icm_rans_decoder_create", "icm_rans_decoder_destroy",
              "icm_rans_decoder_set_streams", "icm_rans_decoder_status", "icm_set_conv_sm_limit", "icm_set_decoder_streams_per_cta", "icm_set_decoder_layout"}
 
@@ -139,6 +139,7 @@ def _load():
         "icm_last_error": (C.c_char_p, []),
         "icm_abi_version": (I, []),
         "icm_launch_count": (I64, []),
+        "icm_note_graph_launches": (I64, [I64]),
         "icm_pmf_to_quantized_cdf": (I, [P, I, I, P]),
         "icm_tables_create": (I, [P, I, I, P, P, C.POINTER(P)]),
         "icm_tables_destroy": (None, [P]),

@@ -247,13 +247,11 @@ class ChannelContextCodec(CompressionModel):
             t.record_stream(torch.cuda.current_stream())
         return t
 
-    def _compress_part(self, x, phase=None, worst_case=False):
-        """compress() of one micro-batch, fully asynchronous: device-resident streams.  `phase("begin"/"end")`
-        brackets the throughput-bound part (transforms + slice loop); the rANS encoders run after "end"."""
+    def _compress_transforms(self, x):
+        """The throughput-bound half of compress(): analysis, hyper-prior, slice loop.  Returns the symbol / index planes of y and
+        z in stream order (int32 [B, n]) and the z shape; asynchronous, no host logic that depends on device data."""
         eb = self.entropy_bottleneck
         B = x.shape[0]
-        if phase:
-            phase("begin")
         y, h, w = self._analysis(x)
         z, zh, zw = self._hyper_analysis(y, B, h, w)
         Pz, Zc = zh * zw, self.hyper_channels
@@ -265,10 +263,23 @@ class ChannelContextCodec(CompressionModel):
               "icm_eb_process")
         mean_sup, scale_sup = self._hyper_synthesis(z_hat, B, zh, zw)
         _, sym, idx = self._slice_loop("compress", B, h, w, mean_sup, scale_sup, y=y)
+        return sym, idx, z_sym, z_idx, zh, zw
+
+    def _compress_encode(self, sym, idx, z_sym, z_idx, worst_case=False):
+        """The latency-bound half: both rANS encoders, device-resident streams ((packed uint8, sizes int32[B+1]) each)."""
+        z_str = ans.encode_streams(self.entropy_bottleneck.device_tables(), z_sym, z_idx, return_device="async", worst_case=worst_case)
+        y_str = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device="async", worst_case=worst_case)
+        return y_str, z_str
+
+    def _compress_part(self, x, phase=None, worst_case=False):
+        """compress() of one micro-batch, fully asynchronous: device-resident streams.  `phase("begin"/"end")`
+        brackets the throughput-bound part (transforms + slice loop); the rANS encoders run after "end"."""
+        if phase:
+            phase("begin")
+        sym, idx, z_sym, z_idx, zh, zw = self._compress_transforms(x)
         if phase:
             phase("end")
-        z_str = ans.encode_streams(eb.device_tables(), z_sym, z_idx, return_device="async", worst_case=worst_case)
-        y_str = ans.encode_streams(self.gaussian_conditional.device_tables(), sym, idx, return_device="async", worst_case=worst_case)
+        y_str, z_str = self._compress_encode(sym, idx, z_sym, z_idx, worst_case)
         return {"y": y_str, "z": z_str, "shape": (zh, zw), "retry": (sym, idx, z_sym, z_idx)}
 
     @torch.no_grad()

@@ -32,8 +32,17 @@ class RoundTripPipeline:
     up to `lag` other jobs run beside them.  Without the chain all jobs start in lockstep, reach their coders
     together and leave the GPU idle (measured run-to-run spread 400-530 images/s)."""
 
-    def __init__(self, model, n_streams=12, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=8, chains=2, decode_priority=False):
+    def __init__(self, model, n_streams=12, part=32, conv_sm_limit=None, decoder_streams_per_cta=8, lag=8, chains=2, decode_priority=False,
+                 cuda_graphs=False):
         self.model = model
+        # cuda_graphs: a job's ~340 launches are captured once per (stream slot, job shape) as four CUDA graphs -- compress
+        # transforms, encoders, decode loop, synthesis (the event-chain hand-overs and the host copies stay between them) -- and
+        # replayed: ~8 ms of host time per job become ~0.3 ms, which is what small jobs (8 images per GPU) and the host-facing
+        # path are bound by.  The first job of a slot runs eagerly (packs weights, sizes the allocator); results are identical.
+        self.cuda_graphs = bool(cuda_graphs)
+        self._job_graphs = {}
+        self._eager_runs = {}
+        self._flag = None
         self.decoder_streams_per_cta = int(decoder_streams_per_cta)
         # SMs the persistent conv / MLP kernels may occupy.  0 = all: the conv kernel's tile scheduler is dynamic, so a CTA
         # that finds its SM held by a decoder CTA (~190 KB of shared memory: they cannot share an SM) simply starts late
@@ -59,6 +68,8 @@ class RoundTripPipeline:
             self._streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)]
             self._hi = [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.n_streams)] if self.decode_priority else None
             self._decoders = {}
+            self._job_graphs, self._eager_runs = {}, {}
+            self._flag = torch.zeros(1, dtype=torch.int32, device=device)  # persistent: captured graphs fold their statuses into it
 
     def _decoder_pair(self, slot, n):
         from compressai import ans
@@ -67,6 +78,40 @@ class RoundTripPipeline:
         if key not in self._decoders:
             self._decoders[key] = (ans.StreamDecoder(n), ans.StreamDecoder(n))
         return self._decoders[key]
+
+    def _capture_job(self, slot, n, x_shape, host_io):
+        """Capture the four graphs of one job on its slot's streams; static tensors link them (shared memory pool)."""
+        import types
+
+        m = self.model
+        dev = self._flag.device
+        ns = self._streams[slot]
+        hs = self._hi[slot] if self._hi is not None else ns
+        jg = types.SimpleNamespace()
+        jg.x = torch.zeros(x_shape, dtype=torch.float32, device=dev)
+        pool = torch.cuda.graph_pool_handle()
+        jg.g_t, jg.g_e, jg.g_d, jg.g_s = (torch.cuda.CUDAGraph() for _ in range(4))
+        n0 = lib().icm_launch_count()
+        with torch.cuda.graph(jg.g_t, pool=pool, stream=ns):
+            jg.sym, jg.idx, jg.z_sym, jg.z_idx, jg.zh, jg.zw = m._compress_transforms(jg.x)
+        with torch.cuda.graph(jg.g_e, pool=pool, stream=ns):
+            jg.y_str, jg.z_str = m._compress_encode(jg.sym, jg.idx, jg.z_sym, jg.z_idx, False)
+        if host_io:  # the streams come back from the host into static device buffers
+            jg.y_in = tuple(torch.zeros_like(t) for t in jg.y_str)
+            jg.z_in = tuple(torch.zeros_like(t) for t in jg.z_str)
+        else:
+            jg.y_in, jg.z_in = jg.y_str, jg.z_str
+        decs = self._decoder_pair(slot, n)
+        with torch.cuda.graph(jg.g_d, pool=pool, stream=hs):
+            jg.y_hat, _ = m._decode_part(jg.y_in, jg.z_in, n, jg.zh, jg.zw, True, decoders=decs)
+            for d in decs:
+                d.fold_status(self._flag)
+        with torch.cuda.graph(jg.g_s, pool=pool, stream=ns):
+            jg.x_hat = m._synthesis(jg.y_hat, n, 4 * jg.zh, 4 * jg.zw, clamp=True)
+        # kernels of the library recorded in the four graphs: reported on every replay so that icm_launch_count keeps counting
+        # kernels that ran (the capture pass itself is counted once although it only records)
+        jg.kernels = int(lib().icm_launch_count() - n0)
+        return jg
 
     def _pin(self, shape, dtype):
         """A pinned staging buffer from the pool (returned by _unpin once its job's strings have been built).  The first request
@@ -128,7 +173,8 @@ class RoundTripPipeline:
             limit = max(sms // 2, sms - decoding * ((self.part + per - 1) // per))
         check(lib().icm_set_conv_sm_limit(int(limit)), "icm_set_conv_sm_limit")
         check(lib().icm_set_decoder_streams_per_cta(self.decoder_streams_per_cta), "icm_set_decoder_streams_per_cta")
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)  # min over every encoder size / decoder status of the call
+        flag = self._flag  # min over every encoder size / decoder status of the call
+        flag.zero_()
         for st in self._streams:
             st.wait_stream(cur)
             flag.record_stream(st)
@@ -146,10 +192,52 @@ class RoundTripPipeline:
 
         lag = self.lag if self.chains else 0
 
+        def front_graph(t, jg):  # the same job replayed from its captured graphs
+            bi, lo, hi = jobs[t]
+            slot = t % self.n_streams
+            ns = self._streams[slot]
+            hs = self._hi[slot] if self._hi is not None else ns
+            with torch.cuda.stream(ns):
+                jg.x.copy_(batches[bi][lo:hi], non_blocking=True)
+                hook = self._phase(t % self.chains) if self.chains else None
+                if hook:
+                    hook("begin")
+                jg.g_t.replay()
+                if hook:
+                    hook("end")
+                jg.g_e.replay()
+                if host_io:
+                    hy, hz = self._pin(jg.y_str[0].shape, torch.uint8), self._pin(jg.z_str[0].shape, torch.uint8)
+                    hsy, hsz = self._pin(jg.y_str[1].shape, torch.int32), self._pin(jg.z_str[1].shape, torch.int32)
+                    for h_, d_ in ((hy, jg.y_str[0]), (hz, jg.z_str[0]), (hsy, jg.y_str[1]), (hsz, jg.z_str[1])):
+                        h_.copy_(d_, non_blocking=True)
+                    for d_, h_ in ((jg.y_in[0], hy), (jg.z_in[0], hz), (jg.y_in[1], hsy), (jg.z_in[1], hsz)):
+                        d_.copy_(h_, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(ns)
+                    pending.append((ev, bi, hy, hsy, hz, hsz))
+                if hs is not ns:
+                    hs.wait_stream(ns)
+                    with torch.cuda.stream(hs):
+                        jg.g_d.replay()
+                    ns.wait_stream(hs)
+                else:
+                    jg.g_d.replay()
+            decoded[t] = (jg, jg.zh, jg.zw)
+            lib().icm_note_graph_launches(jg.kernels)
+
         def front(t):  # C phase + encoders + decode loop of job t
             bi, lo, hi = jobs[t]
             slot = t % self.n_streams
             x = batches[bi]
+            if self.cuda_graphs and not worst_case:
+                key = (slot, hi - lo, tuple(x.shape[1:]), bool(host_io))
+                jg = self._job_graphs.get(key)
+                if jg is None and self._eager_runs.get(key, 0) >= 1:
+                    jg = self._job_graphs[key] = self._capture_job(slot, hi - lo, (hi - lo,) + tuple(x.shape[1:]), host_io)
+                if jg is not None:
+                    return front_graph(t, jg)
+                self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
             with torch.cuda.stream(self._streams[slot]):
                 xd = x[lo:hi].to(dev, non_blocking=True) if host_io else x[lo:hi]
                 c = m._compress_part(xd, phase=self._phase(t % self.chains) if self.chains else None, worst_case=worst_case)
@@ -190,7 +278,11 @@ class RoundTripPipeline:
                 hook = self._phase(t % self.chains) if self.chains else None
                 if hook:
                     hook("begin")
-                x_hat = m._synthesis(y_hat, hi - lo, 4 * zh, 4 * zw, clamp=True)
+                if isinstance(y_hat, torch.Tensor):
+                    x_hat = m._synthesis(y_hat, hi - lo, 4 * zh, 4 * zw, clamp=True)
+                else:  # a captured job: its synthesis graph writes the job's static x_hat
+                    y_hat.g_s.replay()
+                    x_hat = y_hat.x_hat if (out_host is not None or not keep_outputs) else y_hat.x_hat.clone()
                 if hook:
                     hook("end")
                 if out_host is not None:

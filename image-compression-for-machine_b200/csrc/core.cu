@@ -55,6 +55,11 @@ void set_persistent_grid_limit(int n) { g_persistent_sm_limit = n; }
 extern "C" const char *icm_last_error(void) { return icm::g_error; }
 extern "C" int icm_abi_version(void) { return 1; }
 extern "C" int64_t icm_launch_count(void) { return icm::g_launches.load(); }
+extern "C" int64_t icm_note_graph_launches(int64_t n)
+{
+    if (n > 0) icm::g_launches.fetch_add(n, std::memory_order_relaxed);
+    return icm::g_launches.load();
+}
 
 // Frequencies are rounded in float32 (the reference rounds `float p * (1 << precision)`), rescaled to sum
 // to 2^precision by integer division, and zero-width bins are repaired by taking one count from the

@@ -37,6 +37,9 @@ const char *icm_last_error(void);
 int icm_abi_version(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches). */
 int64_t icm_launch_count(void);
+/* A caller that replays this library's kernels from a CUDA graph it captured (compressai/utils/pipeline.py) reports the
+ * number of kernel nodes of each replay here, so that icm_launch_count keeps counting kernels that ran, not API calls. */
+int64_t icm_note_graph_launches(int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * R5  compressai._CXX.pmf_to_quantized_cdf(list[float] pmf, int precision) -> list[int]

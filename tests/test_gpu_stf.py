@@ -233,6 +233,36 @@ def test_stream_pipeline_equals_plain_api(model, chains, lag):
         assert strings[k][0] == c["strings"][0] and strings[k][1] == c["strings"][1]
 
 
+@pytest.mark.parametrize("priority", [False, True])
+def test_stream_pipeline_with_cuda_graphs_equals_plain_api(model, priority):
+    """RoundTripPipeline(cuda_graphs=True): the first job of a (slot, shape) runs eagerly, the second is captured as four
+    CUDA graphs and from then on replayed; every pass -- eager, capturing, replaying; device-resident and host I/O -- must give
+    the plain API's strings and reconstructions, for different images each time (static buffers are refilled, not reused)."""
+    from compressai.utils.pipeline import RoundTripPipeline
+    from oracle import weights
+
+    pipe = RoundTripPipeline(model, n_streams=3, part=4, decoder_streams_per_cta=4, lag=2, chains=2, decode_priority=priority, cuda_graphs=True)
+    for rnd in range(4):
+        batches = [torch.cat([weights.seeded_image((1, 3, 64, 128), seed=500 + 100 * rnd + 7 * k + s) for s in range(8)]) for k in range(3)]
+        dev_batches = [b.cuda() for b in batches]
+        host = rnd % 2 == 1
+        if host:
+            outs = [torch.empty_like(b).pin_memory() for b in batches]
+            _, strings = pipe.roundtrip([b.pin_memory() for b in batches], host_io=True, out_host=outs)
+            torch.cuda.synchronize()
+        else:
+            x_hats, _ = pipe.roundtrip(dev_batches)
+        for k, xb in enumerate(dev_batches):
+            c = model.compress(xb)
+            d = model.decompress(c["strings"], c["shape"])
+            if host:
+                assert torch.equal(outs[k], d["x_hat"].cpu()), (rnd, k)
+                assert strings[k][0] == c["strings"][0] and strings[k][1] == c["strings"][1], (rnd, k)
+            else:
+                assert torch.equal(x_hats[k], d["x_hat"]), (rnd, k)
+    assert len(pipe._job_graphs) >= 3  # graphs were captured and used
+
+
 def test_full_size_stream_sizes_track_the_reference(model, golden_dir):
     """The 768x512 image whose reference strings are recorded in tests/golden/stf_full.json: same latent shape, stream sizes
     within a few percent (bf16 transforms), decompress(compress(x)) == clamp(forward(x))."""
