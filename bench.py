@@ -417,6 +417,8 @@ def main():
                "d2h_bytes_per_step": out_host.numel() * 4 + pipe_capacity_bytes(B), "ms_per_step": round(ms_e2e / args.steps, 3),
                "timing": "wall clock around K pipelined steps incl. creation of the Python byte strings"}
 
+    pipe.release_graphs()  # their private memory pools go back to the allocator before further pipelines are built
+    torch.cuda.empty_cache()
     # the same pipeline with the survey's stress weights: many CDF tables in use, ~26 % escape symbols (the coder's hard case)
     stress = None
     if not args.no_stress and args.weights != "stress":

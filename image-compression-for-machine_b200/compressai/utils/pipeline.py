@@ -79,8 +79,20 @@ class RoundTripPipeline:
             self._decoders[key] = (ans.StreamDecoder(n), ans.StreamDecoder(n))
         return self._decoders[key]
 
-    def _capture_job(self, slot, n, x_shape, host_io):
-        """Capture the four graphs of one job on its slot's streams; static tensors link them (shared memory pool)."""
+    def release_graphs(self):
+        """Drop every captured job graph (and with it the graphs' private memory pools: ~2-4 GB per stream slot at 32 images of
+        768x512); the next jobs run eagerly once and are captured again."""
+        self._job_graphs, self._eager_runs = {}, {}
+
+    def _may_capture(self):
+        """Graph pools are private memory: capture only while at least a third of the device memory is free."""
+        free, total = torch.cuda.mem_get_info(self._flag.device)
+        return free * 3 >= total
+
+    def _capture_job(self, slot, n, x_shape):
+        """Capture the four graphs of one job on its slot's streams; static tensors link them (shared memory pool).  The decode
+        graph reads the streams where the encode graph left them: with host I/O they travel to pinned host memory and back
+        into the same device buffers, so one set of graphs serves both modes."""
         import types
 
         m = self.model
@@ -96,11 +108,7 @@ class RoundTripPipeline:
             jg.sym, jg.idx, jg.z_sym, jg.z_idx, jg.zh, jg.zw = m._compress_transforms(jg.x)
         with torch.cuda.graph(jg.g_e, pool=pool, stream=ns):
             jg.y_str, jg.z_str = m._compress_encode(jg.sym, jg.idx, jg.z_sym, jg.z_idx, False)
-        if host_io:  # the streams come back from the host into static device buffers
-            jg.y_in = tuple(torch.zeros_like(t) for t in jg.y_str)
-            jg.z_in = tuple(torch.zeros_like(t) for t in jg.z_str)
-        else:
-            jg.y_in, jg.z_in = jg.y_str, jg.z_str
+        jg.y_in, jg.z_in = jg.y_str, jg.z_str
         decs = self._decoder_pair(slot, n)
         with torch.cuda.graph(jg.g_d, pool=pool, stream=hs):
             jg.y_hat, _ = m._decode_part(jg.y_in, jg.z_in, n, jg.zh, jg.zw, True, decoders=decs)
@@ -231,10 +239,10 @@ class RoundTripPipeline:
             slot = t % self.n_streams
             x = batches[bi]
             if self.cuda_graphs and not worst_case:
-                key = (slot, hi - lo, tuple(x.shape[1:]), bool(host_io))
+                key = (slot, hi - lo, tuple(x.shape[1:]))
                 jg = self._job_graphs.get(key)
-                if jg is None and self._eager_runs.get(key, 0) >= 1:
-                    jg = self._job_graphs[key] = self._capture_job(slot, hi - lo, (hi - lo,) + tuple(x.shape[1:]), host_io)
+                if jg is None and self._eager_runs.get(key, 0) >= 1 and self._may_capture():
+                    jg = self._job_graphs[key] = self._capture_job(slot, hi - lo, (hi - lo,) + tuple(x.shape[1:]))
                 if jg is not None:
                     return front_graph(t, jg)
                 self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
