@@ -72,6 +72,47 @@ def test_layouts_agree(gc):
     assert torch.equal(bf[:, 16:].float(), cl(y_hat).bfloat16().float()) and torch.all(bf[:, :16] == 0)
 
 
+def _indexes_channels_last(scales_flat, table, bound=0.11):
+    """icm_gc_build_indexes on a channels-last [1, P, 32] view (the vectorised kernel's layout) -> flat indexes."""
+    from compressai._native import check, lib, stream_ptr, view_bcp
+
+    n = scales_flat.numel()
+    P = -(-n // 32)
+    sc = torch.full((P * 32,), 1.0, device="cuda")
+    sc[:n] = scales_flat
+    sc = sc.reshape(P, 32).contiguous()
+    idx = torch.empty(1, 32 * P, dtype=torch.int32, device="cuda")
+    check(lib().icm_gc_build_indexes(view_bcp(sc, 1, 32, P), 1, 32, P, table.data_ptr(), table.numel(), bound, idx.data_ptr(), 32 * P, 0, stream_ptr()))
+    return idx.reshape(32, P).t().reshape(-1)[:n]
+
+
+def test_vectorised_index_lookup_is_exact_on_every_table_edge(gc, golden_dir):
+    """The channels-last kernels resolve build_indexes with a two-probe lookup (bit-pattern bins + one compare) instead of
+    the binary search.  It must give the reference's index (entropy_models.py:661-666) on the KAT scales -- every table
+    value and its two fp32 neighbours, 0, -1, 0.11, 256, 1e9 -- on inf / NaN, and fall back to the search for tables the
+    lookup cannot serve (two levels in one bin, more than 256 bins)."""
+    g = np.load(os.path.join(golden_dir, "entropy_kat.npz"))
+    tab = gc.scale_table_device(torch.device("cuda"))
+    scales = torch.from_numpy(g["scales"]).cuda()
+    got = _indexes_channels_last(scales, tab)
+    assert np.array_equal(got.cpu().numpy(), g["indexes"])
+    special = torch.tensor([float("inf"), float("nan"), -float("inf"), -0.0, 1e-30, 3e38], device="cuda")
+    ref = gc.build_indexes(special.reshape(1, 1, -1)).reshape(-1)  # generic kernel (binary search)
+    assert torch.equal(_indexes_channels_last(special, tab), ref)
+    # without the lower bound negative scales reach the lookup itself
+    neg = torch.tensor([-5.0, -0.11, 0.0, 0.05, 0.2, 300.0, float("nan")], device="cuda")
+    t = tab.cpu()
+    want = torch.tensor([int((t[:-1] < v).sum()) if v == v else len(t) - 1 for v in neg.cpu()], dtype=torch.int32)
+    assert torch.equal(_indexes_channels_last(neg, tab, bound=-1e30).cpu(), want)
+    # tables the lookup must refuse: levels 1 % apart (several per bin) and a range of > 256 bins
+    torch.manual_seed(1)
+    s = torch.exp(torch.empty(4000, device="cuda").uniform_(-12, 12))
+    for t2 in (torch.exp(torch.linspace(-1.0, 1.0, 200)), torch.exp(torch.linspace(-11.0, 11.0, 40))):
+        t2 = t2.float().cuda().contiguous()
+        want = torch.tensor([int((t2[:-1] < v).sum()) for v in torch.maximum(s, torch.tensor(0.11, device="cuda"))], dtype=torch.int32)
+        assert torch.equal(_indexes_channels_last(s, t2).cpu(), want)
+
+
 def test_entropy_bottleneck_kats(golden_dir):
     from compressai.entropy_models import EntropyBottleneck
     from oracle import weights

@@ -49,3 +49,20 @@ run("gc_quantize_index", lambda: check(L.icm_gc_quantize_index(view_bcp(y, B, Z,
                                                               table.data_ptr(), table.numel(), 0.11, sym.data_ptr(), idx.data_ptr(), M * P, Z * P * i,
                                                               view_bcp(y_hat, B, Z, P, Z * i), view_bcp(sup, B, Z, P, M), NULL_VIEW, st)), n * 24)
 run("add_lrp", lambda: check(L.icm_add_lrp(view_bcp(y_hat, B, Z, P, Z * i), view_bcp(mu, B, Z, P), B, Z, P, view_bcp(sup, B, Z, P, M), NULL_VIEW, st)), n * 14)
+
+# the grouped tail step of round 2: slices 6..11 in ONE launch (C = 192 channels; 445 MB per launch at B = 64, more than the
+# 126 MB L2, so back-to-back launches on the same buffers are served from HBM)
+C6 = 6 * Z
+n6 = B * C6 * P
+musc = torch.randn(B * P, 2 * C6, device=dev, generator=g).abs() + 0.05
+sup12 = torch.zeros(B * P, M + Z * 12, device=dev, dtype=torch.bfloat16)
+lrp6 = torch.randn(B * P, C6, device=dev, generator=g) * 0.1
+run("gc_quantize_index x6", lambda: check(L.icm_gc_quantize_index(view_bcp(y, B, C6, P, C6), view_bcp(musc, B, C6, P), view_bcp(musc, B, C6, P, C6), B, C6, P,
+                                                                 table.data_ptr(), table.numel(), 0.11, sym.data_ptr(), idx.data_ptr(), M * P, C6 * P,
+                                                                 view_bcp(y_hat, B, C6, P, C6), view_bcp(sup12, B, C6, P, M + C6), NULL_VIEW, st)), n6 * 24)
+run("add_lrp x6", lambda: check(L.icm_add_lrp(view_bcp(y_hat, B, C6, P, C6), view_bcp(lrp6, B, C6, P), B, C6, P, NULL_VIEW, NULL_VIEW, st)), n6 * 12)
+idx6 = torch.zeros(B, C6 * P, device=dev, dtype=torch.int32)
+run("gc_build_indexes x6", lambda: check(L.icm_gc_build_indexes(view_bcp(musc, B, C6, P, C6), B, C6, P, table.data_ptr(), table.numel(), 0.11,
+                                                               idx6.data_ptr(), C6 * P, 0, st)), n6 * 8)
+run("gc_dequantize x6", lambda: check(L.icm_gc_dequantize(idx6.data_ptr(), C6 * P, 0, view_bcp(musc, B, C6, P), B, C6, P, view_bcp(y_hat, B, C6, P, C6),
+                                                         view_bcp(sup12, B, C6, P, M + C6), NULL_VIEW, st)), n6 * 14)
