@@ -192,27 +192,41 @@ def test_eval_forward_still_runs_the_inference_kernels_after_training_steps():
 
 
 def test_cuda_graph_step_equals_eager_step():
-    """Trainer(cuda_graph=True): the captured step replays forward, backward, clipping and both Adams; with the same CUDA
-    generator seed it must follow the eager trajectory (same kernels, same order) and the warm-up steps of the capture must
-    leave no trace in the optimizer state."""
+    """Trainer(cuda_graph=True): the captured step replays forward, backward, clipping and both Adams.  With the randomness
+    switched off (a TrainRng that returns zero noise and keep-masks of ones, drawn on the device so that it is capturable) the
+    replayed trajectory must equal the eager one -- same kernels in the same order -- and the three warm-up steps the capture
+    runs must leave no trace in the parameters, the Adam moments or the step counter."""
+    from compressai.models._train import TrainRng
     from compressai.training import Trainer
     from oracle import weights
+
+    class NoRandomness(TrainRng):
+        def uniform(self, like):
+            return torch.zeros_like(like)
+
+        def keep_mask(self, like, keep):
+            return like.new_ones((like.shape[0], 1, 1))
 
     _strict_fp32()
     x = weights.seeded_image((2, 3, 64, 64), seed=5).cuda()
     traj = []
     for graph in (False, True):
         m = _stf()
+        m.train_rng = NoRandomness()
         tr = Trainer(m, lmbda=800.0, learning_rate=1e-4, cuda_graph=graph)
         losses = []
         for step in range(3):
             crit = tr.step(x)
-            losses.append(float(crit["loss"].item()))
-        traj.append((losses, float(tr.optimizer._state[0].item()), tr.optimizer.param.detach().clone()))
-    (le, te, pe), (lg, tg, pg) = traj
+            losses.append((float(crit["loss"].item()), float(crit["aux_loss"].item())))
+        traj.append((losses, float(tr.optimizer._state[0].item()), tr.optimizer.param.detach().clone(), tr.aux_optimizer.param.detach().clone()))
+    (le, te, pe, qe), (lg, tg, pg, qg) = traj
     assert te == tg == 3.0
-    # the random draws differ (the graph's generator offsets are its own), so compare the trajectories statistically:
-    # same starting loss scale, both decreasing, parameters moved by comparable amounts
-    assert abs(le[0] - lg[0]) <= 0.2 * abs(le[0])
-    moved_e, moved_g = float((pe - pg).abs().max()), float(pe.abs().max())
-    assert moved_e <= 10 * 3 * 1e-4 and moved_g > 0
+    for (a, b), (c, d) in zip(le, lg):
+        assert abs(a - c) <= 1e-4 * abs(a) and abs(b - d) <= 1e-4 * abs(b), (le, lg)
+    assert le[2][0] < le[0][0]  # it trains
+    # library backward kernels reduce with atomics, so gradients that are ~0 can change sign between two runs and Adam's first
+    # steps move such an element by +-lr either way: compare the bulk, not the worst element
+    d = (pe - pg).abs()
+    print("graph vs eager: mean |dp| %.3g, fraction > 1e-5: %.4f, max %.3g" % (float(d.mean()), float((d > 1e-5).float().mean()), float(d.max())))
+    assert float(d.mean()) <= 2e-6 and float((d > 1e-5).float().mean()) <= 0.02, (float(d.mean()), float((d > 1e-5).float().mean()))
+    assert float((qe - qg).abs().mean()) <= 1e-5  # a quantile whose gradient is ~0 may take its +-lr step either way
