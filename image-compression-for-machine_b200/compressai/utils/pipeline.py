@@ -82,6 +82,8 @@ class RoundTripPipeline:
     def release_graphs(self):
         """Drop every captured job graph (and with it the graphs' private memory pools: ~2-4 GB per stream slot at 32 images of
         768x512); the next jobs run eagerly once and are captured again."""
+        if self._job_graphs:
+            torch.cuda.synchronize()  # no replay may still be running on the pools that are about to be freed
         self._job_graphs, self._eager_runs = {}, {}
 
     def _may_capture(self):

@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float *__restric
                                                           const float *__restrict__ beta, float *__restrict__ tokens,
                                                           int B, int H, int W, int C)
 {
-    __shared__ float s_w[64 * 12], s_b[64], s_g[64], s_be[64];
+    __shared__ __align__(16) float s_w[64 * 12];
+    __shared__ float s_b[64], s_g[64], s_be[64];
     extern __shared__ float s_o[]; // [blockDim.x][C + 1]
     for (int i = threadIdx.x; i < C * 12; i += blockDim.x) s_w[i] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_b[i] = bias[i]; s_g[i] = gamma[i]; s_be[i] = beta[i]; }
@@ -247,8 +248,13 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float *__restric
         float a = 0.f;
         if (c < C) {
             a = s_b[c];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) a += s_w[c * 12 + k] * x[k];
+            // the 12 weights of a channel as three broadcast LDS.128 (one LDS.32 per multiply-add made the kernel LSU-bound:
+            // 0.91 ms for 64 images at 1.6 TB/s); same accumulation order as before
+            const float4 *w4 = reinterpret_cast<const float4 *>(s_w + c * 12);
+            const float4 wa = w4[0], wb = w4[1], wc = w4[2];
+            a += wa.x * x[0]; a += wa.y * x[1]; a += wa.z * x[2]; a += wa.w * x[3];
+            a += wb.x * x[4]; a += wb.y * x[5]; a += wb.z * x[6]; a += wb.w * x[7];
+            a += wc.x * x[8]; a += wc.y * x[9]; a += wc.z * x[10]; a += wc.w * x[11];
             sum += a;
         }
         y[c] = a;
@@ -269,7 +275,14 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float *__restric
     const long long first = (long long)blockIdx.x * blockDim.x;
     const int n_tok = (int)min((long long)blockDim.x, total - first);
     float *dst = tokens + first * C;
-    for (int i = threadIdx.x; i < n_tok * C; i += blockDim.x) dst[i] = s_o[(i / C) * (C + 1) + (i % C)];
+    // (row, column) walk without a division per element: i advances by blockDim.x = q * C + r
+    const int q = blockDim.x / C, r = blockDim.x - q * C;
+    int row = threadIdx.x / C, col = threadIdx.x - row * C;
+    for (int i = threadIdx.x; i < n_tok * C; i += blockDim.x) {
+        dst[i] = s_o[row * (C + 1) + col];
+        row += q; col += r;
+        if (col >= C) { col -= C; ++row; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
