@@ -179,6 +179,8 @@ def _load():
         "icm_pack_deconv_weight": (I, [P, I, I, I, I, P, P]),
         "icm_gc_train_forward": (I, [Rows, Rows, Rows, Rows, I64, I64, F, F, Rows, Rows, P]),
         "icm_gc_train_backward": (I, [Rows, Rows, Rows, Rows, Rows, Rows, I64, I64, F, F, Rows, Rows, Rows, P]),
+        "icm_layernorm_train_forward": (I, [P, P, P, P, I, P, P, I64, I, P]),
+        "icm_layernorm_train_backward": (I, [P, P, I, P, P, P, P, P, P, I64, I, P]),
         "icm_grad_sumsq": (I, [P, I64, P, P]),
         "icm_clip_coef": (I, [P, F, F, P, P, P]),
         "icm_adam_step": (I, [P, P, P, P, I64, F, F, F, F, I, P, P, F, P]),

@@ -80,6 +80,52 @@ class _GaussianTrain(torch.autograd.Function):
         return g_y, g_mu, g_s, None, None, None
 
 
+class _LayerNormTrain(torch.autograd.Function):
+    """nn.LayerNorm forward / backward as one kernel each (csrc/train.cu) instead of torch's three; emits bf16 directly under
+    autocast (the consumer is always a linear layer)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_bf16):
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C)
+        if x2.dtype != torch.float32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        rows = x2.shape[0]
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty((rows, C), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+        mean, rstd = torch.empty(rows, dtype=torch.float32, device=x.device), torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(lib().icm_layernorm_train_forward(x2.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 0 if out_bf16 else 1, mean.data_ptr(),
+                                                rstd.data_ptr(), rows, C, stream_ptr()), "icm_layernorm_train_forward")
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w, mean, rstd = ctx.saved_tensors
+        rows, C = x2.shape
+        g2 = g.reshape(rows, C)
+        if g2.dtype not in (torch.float32, torch.bfloat16):
+            g2 = g2.float()
+        g2 = g2.contiguous()
+        dx = torch.empty_like(x2)
+        dg, db = torch.empty(C, dtype=torch.float32, device=x2.device), torch.empty(C, dtype=torch.float32, device=x2.device)
+        check(lib().icm_layernorm_train_backward(x2.data_ptr(), g2.data_ptr(), 0 if g2.dtype == torch.bfloat16 else 1, w.data_ptr(), mean.data_ptr(),
+                                                 rstd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C, stream_ptr()),
+              "icm_layernorm_train_backward")
+        return dx.view(ctx.shape), dg, db, None
+
+
+def layer_norm(x, norm, fused=True, fp32_out=False):
+    """LayerNorm over the last dimension with the module's parameters; fused kernels on CUDA, the PyTorch operator otherwise
+    (fused=False: the comparison the tests make).  Under autocast the fused form emits bf16 (its consumer is a linear layer)
+    unless fp32_out (the patch embedding's LayerNorm starts the fp32 residual stream)."""
+    C = x.shape[-1]
+    if fused and x.is_cuda and C % 4 == 0 and C <= 768:
+        return _LayerNormTrain.apply(x, norm.weight, norm.bias, torch.is_autocast_enabled() and not fp32_out)
+    return F.layer_norm(x, (C,), norm.weight, norm.bias)
+
+
 def gaussian_train(gc, y, mu, scale, noise):
     """GaussianConditional(y, scale, mu) in training mode -> (likelihood, straight-through y_hat)."""
     lb = gc.likelihood_bound if gc.use_likelihood_bound else 0.0
@@ -135,15 +181,15 @@ def _drop_path(t, rate, rng):
     return t * rng.keep_mask(t, keep).to(t.dtype) / keep
 
 
-def _stage(layer, x, H, W, rates, rng):
+def _stage(layer, x, H, W, rates, rng, fused=True):
     """BasicLayer (stf.py:308-347): x [B, H*W, C] tokens."""
     B, _, C = x.shape
     ws = layer.blocks[0].window_size
     mask = _shift_mask(H, W, ws, ws // 2, x.device) if len(layer.blocks) > 1 else None
     for blk, rate in zip(layer.blocks, rates):
-        a = _window_attention(blk.attn, F.layer_norm(x, (C,), blk.norm1.weight, blk.norm1.bias).view(B, H, W, C), H, W, ws, blk.shift_size, mask)
+        a = _window_attention(blk.attn, layer_norm(x, blk.norm1, fused).view(B, H, W, C), H, W, ws, blk.shift_size, mask)
         x = x + _drop_path(a.reshape(B, H * W, C), rate, rng)
-        h = F.layer_norm(x, (C,), blk.norm2.weight, blk.norm2.bias)
+        h = layer_norm(x, blk.norm2, fused)
         h = F.linear(F.gelu(F.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias)), blk.mlp.fc2.weight, blk.mlp.fc2.bias)
         x = x + _drop_path(h, rate, rng)
     ds = layer.downsample
@@ -155,9 +201,9 @@ def _stage(layer, x, H, W, rates, rng):
             g = F.pad(g, (0, 0, 0, W % 2, 0, H % 2))
         g = torch.cat([g[:, 0::2, 0::2], g[:, 1::2, 0::2], g[:, 0::2, 1::2], g[:, 1::2, 1::2]], -1)
         H, W = (H + 1) // 2, (W + 1) // 2
-        g = F.layer_norm(g.reshape(B, H * W, 4 * C), (4 * C,), ds.norm.weight, ds.norm.bias)
+        g = layer_norm(g.reshape(B, H * W, 4 * C), ds.norm, fused)
         return F.linear(g, ds.reduction.weight).float(), H, W  # the residual stream stays fp32 under autocast
-    g = F.linear(F.layer_norm(x, (C,), ds.norm.weight, ds.norm.bias), ds.reduction.weight)  # stf.py:251-260
+    g = F.linear(layer_norm(x, ds.norm, fused), ds.reduction.weight)  # stf.py:251-260
     g = F.pixel_shuffle(g.transpose(1, 2).reshape(B, 2 * C, H, W), 2)
     return g.permute(0, 2, 3, 1).reshape(B, 4 * H * W, C // 2).float(), 2 * H, 2 * W
 
@@ -205,9 +251,9 @@ def stf_train_forward(m, x, rng=None, fused=True):
         x = F.pad(x, (0, 0, 0, 1))
     t = F.conv2d(x, pe.proj.weight, pe.proj.bias, stride=2)
     h, w = t.shape[2], t.shape[3]
-    t = F.layer_norm(t.flatten(2).transpose(1, 2).float(), (m.embed_dim,), pe.norm.weight, pe.norm.bias)
+    t = layer_norm(t.flatten(2).transpose(1, 2).float(), pe.norm, fused, fp32_out=True).float()
     for layer, rates in zip(m.layers, ana_rates):
-        t, h, w = _stage(layer, t, h, w, rates, rng)
+        t, h, w = _stage(layer, t, h, w, rates, rng, fused)
     M, Z = m.latent_channels, 32
     y = t.view(B, h, w, M).permute(0, 3, 1, 2).contiguous()
     z = _conv_stack(m.h_a, y)
@@ -241,7 +287,7 @@ def stf_train_forward(m, x, rng=None, fused=True):
         hats.append(y_hat + 0.5 * torch.tanh(lrp))
     t = torch.cat(hats, 1).permute(0, 2, 3, 1).reshape(B, h * w, M).float()
     for layer, rates in zip(m.syn_layers, syn_rates):
-        t, h, w = _stage(layer, t, h, w, rates, rng)
+        t, h, w = _stage(layer, t, h, w, rates, rng, fused)
     u = t.view(B, h, w, m.embed_dim).permute(0, 3, 1, 2).contiguous()
     x_hat = _conv_stack(m.end_conv, u)
     return {"x_hat": x_hat, "likelihoods": {"y": torch.cat(liks, 1), "z": z_lik}}

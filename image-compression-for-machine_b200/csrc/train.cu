@@ -250,3 +250,189 @@ extern "C" int icm_adam_step(float *d_param, const float *d_grad, float *d_exp_a
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ LayerNorm, training
+// nn.LayerNorm forward + backward for the Swin blocks of the training step (stf.py:155,197,232,256,379; 55 calls per step).
+// torch's own three kernels per call (forward, input gradient, gamma/beta gradient) took 15 ms of an 86 ms step on the
+// [262 144, 48] ... [1 024, 768] token tensors of a 16 x 256 x 256 batch; these move each tensor once.
+//   forward : y = (x - mean) * rstd * gamma + beta, mean / rstd kept per row; y in fp32 or (under autocast) bf16
+//   backward: dx = rstd * (g gamma - mean_c(g gamma) - xhat mean_c(g gamma xhat)); dgamma = sum_rows g xhat; dbeta = sum_rows g
+// LPR lanes share a row (C / 4 float4 chunks dealt round-robin), so a warp works on 32 / LPR rows at once; the per-channel
+// gamma / beta gradients are accumulated in registers over the rows a lane sees, folded per CTA in shared memory and added to
+// global memory with one atomicAdd per channel and CTA (summation order across CTAs is not fixed: fine for training).
+namespace icm {
+
+constexpr int LN_NQ = 6;       // float4 chunks per lane: C <= 4 * 32 * 6 = 768
+constexpr int LN_THREADS = 256;
+
+__device__ __forceinline__ float group_sum(float v, int lpr)
+{
+    for (int o = lpr >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 load4(const void *p, long long elem, int is_bf16)
+{
+    if (!is_bf16) return *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p) + elem);
+    const uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __nv_bfloat16 *>(p) + elem);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(LN_THREADS) ln_train_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                                 const float *__restrict__ beta, void *__restrict__ y, int y_bf16,
+                                                                 float *__restrict__ mean, float *__restrict__ rstd, long long rows, int C,
+                                                                 int lpr)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & (lpr - 1), grp = lane / lpr, gpw = 32 / lpr;
+    const int C4 = C >> 2;
+    const long long stride = (long long)gridDim.x * (LN_THREADS / 32) * gpw;
+    // every lane of a warp must take part in the shuffles: loop on the warp's first row, guard the row itself
+    for (long long base = ((long long)blockIdx.x * (LN_THREADS / 32) + warp) * gpw; base < rows; base += stride) {
+        const long long row = base + grp;
+        const bool live = row < rows;
+        float4 v[LN_NQ];
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < LN_NQ; ++q) {
+            const int c4 = sub + q * lpr;
+            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && c4 < C4) v[q] = *reinterpret_cast<const float4 *>(x + row * C + 4 * c4);
+            s += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+        }
+        const float mu = group_sum(s, lpr) / (float)C;
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < LN_NQ; ++q) {
+            if (sub + q * lpr < C4) {
+                float d;
+                d = v[q].x - mu; ss += d * d; d = v[q].y - mu; ss += d * d; d = v[q].z - mu; ss += d * d; d = v[q].w - mu; ss += d * d;
+            }
+        }
+        const float rs = rsqrtf(group_sum(ss, lpr) / (float)C + 1e-5f);
+        if (!live) continue;
+        if (sub == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+        for (int q = 0; q < LN_NQ; ++q) {
+            const int c4 = sub + q * lpr;
+            if (c4 >= C4) continue;
+            const float4 g = *reinterpret_cast<const float4 *>(gamma + 4 * c4), b = *reinterpret_cast<const float4 *>(beta + 4 * c4);
+            const float4 o = make_float4((v[q].x - mu) * rs * g.x + b.x, (v[q].y - mu) * rs * g.y + b.y, (v[q].z - mu) * rs * g.z + b.z,
+                                         (v[q].w - mu) * rs * g.w + b.w);
+            if (y_bf16) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(y) + row * C + 4 * c4) =
+                    make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+            } else {
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + row * C + 4 * c4) = o;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LN_THREADS) ln_train_bwd_kernel(const float *__restrict__ x, const void *__restrict__ g, int g_bf16,
+                                                                 const float *__restrict__ gamma, const float *__restrict__ mean,
+                                                                 const float *__restrict__ rstd, float *__restrict__ dx,
+                                                                 float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows, int C, int lpr)
+{
+    extern __shared__ float s_acc[]; // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += LN_THREADS) s_acc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & (lpr - 1), grp = lane / lpr, gpw = 32 / lpr;
+    const int C4 = C >> 2;
+    const long long stride = (long long)gridDim.x * (LN_THREADS / 32) * gpw;
+    float4 ag[LN_NQ], ab[LN_NQ], gm[LN_NQ];
+#pragma unroll
+    for (int q = 0; q < LN_NQ; ++q) {
+        ag[q] = ab[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c4 = sub + q * lpr;
+        gm[q] = c4 < C4 ? *reinterpret_cast<const float4 *>(gamma + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long base = ((long long)blockIdx.x * (LN_THREADS / 32) + warp) * gpw; base < rows; base += stride) {
+        const long long row = base + grp;
+        const bool live = row < rows;
+        const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
+        float4 xh[LN_NQ], gg[LN_NQ];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < LN_NQ; ++q) {
+            const int c4 = sub + q * lpr;
+            xh[q] = gg[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && c4 < C4) {
+                const float4 xv = *reinterpret_cast<const float4 *>(x + row * C + 4 * c4);
+                const float4 gv = load4(g, row * C + 4 * c4, g_bf16);
+                xh[q] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                ag[q].x += gv.x * xh[q].x; ag[q].y += gv.y * xh[q].y; ag[q].z += gv.z * xh[q].z; ag[q].w += gv.w * xh[q].w;
+                ab[q].x += gv.x; ab[q].y += gv.y; ab[q].z += gv.z; ab[q].w += gv.w;
+                gg[q] = make_float4(gv.x * gm[q].x, gv.y * gm[q].y, gv.z * gm[q].z, gv.w * gm[q].w);
+                s1 += (gg[q].x + gg[q].y) + (gg[q].z + gg[q].w);
+                s2 += (gg[q].x * xh[q].x + gg[q].y * xh[q].y) + (gg[q].z * xh[q].z + gg[q].w * xh[q].w);
+            }
+        }
+        s1 = group_sum(s1, lpr) / (float)C;
+        s2 = group_sum(s2, lpr) / (float)C;
+        if (!live) continue;
+#pragma unroll
+        for (int q = 0; q < LN_NQ; ++q) {
+            const int c4 = sub + q * lpr;
+            if (c4 >= C4) continue;
+            *reinterpret_cast<float4 *>(dx + row * C + 4 * c4) =
+                make_float4(rs * (gg[q].x - s1 - xh[q].x * s2), rs * (gg[q].y - s1 - xh[q].y * s2), rs * (gg[q].z - s1 - xh[q].z * s2),
+                            rs * (gg[q].w - s1 - xh[q].w * s2));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < LN_NQ; ++q) {
+        const int c4 = sub + q * lpr;
+        if (c4 >= C4) continue;
+        atomicAdd(&s_acc[4 * c4], ag[q].x); atomicAdd(&s_acc[4 * c4 + 1], ag[q].y); atomicAdd(&s_acc[4 * c4 + 2], ag[q].z); atomicAdd(&s_acc[4 * c4 + 3], ag[q].w);
+        atomicAdd(&s_acc[C + 4 * c4], ab[q].x); atomicAdd(&s_acc[C + 4 * c4 + 1], ab[q].y); atomicAdd(&s_acc[C + 4 * c4 + 2], ab[q].z); atomicAdd(&s_acc[C + 4 * c4 + 3], ab[q].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += LN_THREADS) { atomicAdd(dgamma + i, s_acc[i]); atomicAdd(dbeta + i, s_acc[C + i]); }
+}
+
+static int ln_lanes_per_row(int C)
+{
+    int lpr = 4;
+    while (lpr < 32 && lpr < C / 4) lpr *= 2;
+    return lpr;
+}
+
+static unsigned ln_grid(int64_t rows, int lpr, int per_sm)
+{
+    const long long rows_per_cta = (LN_THREADS / 32) * (32 / lpr);
+    long long need = (rows + rows_per_cta - 1) / rows_per_cta, cap = (long long)sm_count() * per_sm;
+    if (need > cap) need = cap;
+    return (unsigned)(need < 1 ? 1 : need);
+}
+
+}  // namespace icm
+
+extern "C" int icm_layernorm_train_forward(const float *d_x, const float *d_gamma, const float *d_beta, void *d_y, int y_dtype,
+                                           float *d_mean, float *d_rstd, int64_t rows, int C, void *stream)
+{
+    ICM_CHECK_ARG(d_x && d_gamma && d_beta && d_y && d_mean && d_rstd, "icm_layernorm_train_forward: null argument");
+    ICM_CHECK_ARG(rows > 0 && C >= 4 && C % 4 == 0 && C <= 4 * 32 * LN_NQ, "icm_layernorm_train_forward: rows=%lld C=%d (C must be a multiple of 4, <= 768)", (long long)rows, C);
+    ICM_CHECK_ARG((((uintptr_t)d_x | (uintptr_t)d_gamma | (uintptr_t)d_beta) & 15) == 0 && ((uintptr_t)d_y & 7) == 0, "icm_layernorm_train_forward: misaligned pointer");
+    const int lpr = ln_lanes_per_row(C);
+    ln_train_fwd_kernel<<<ln_grid(rows, lpr, 16), LN_THREADS, 0, as_stream(stream)>>>(d_x, d_gamma, d_beta, d_y, y_dtype == ICM_OUT_BF16, d_mean, d_rstd, rows, C, lpr);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}
+
+extern "C" int icm_layernorm_train_backward(const float *d_x, const void *d_grad_y, int grad_dtype, const float *d_gamma, const float *d_mean,
+                                            const float *d_rstd, float *d_grad_x, float *d_grad_gamma, float *d_grad_beta, int64_t rows, int C,
+                                            void *stream)
+{
+    ICM_CHECK_ARG(d_x && d_grad_y && d_gamma && d_mean && d_rstd && d_grad_x && d_grad_gamma && d_grad_beta, "icm_layernorm_train_backward: null argument");
+    ICM_CHECK_ARG(rows > 0 && C >= 4 && C % 4 == 0 && C <= 4 * 32 * LN_NQ, "icm_layernorm_train_backward: rows=%lld C=%d", (long long)rows, C);
+    ICM_CHECK_ARG((((uintptr_t)d_x | (uintptr_t)d_gamma | (uintptr_t)d_grad_x) & 15) == 0 && ((uintptr_t)d_grad_y & 7) == 0, "icm_layernorm_train_backward: misaligned pointer");
+    ICM_CUDA(cudaMemsetAsync(d_grad_gamma, 0, (size_t)C * 4, as_stream(stream)));
+    ICM_CUDA(cudaMemsetAsync(d_grad_beta, 0, (size_t)C * 4, as_stream(stream)));
+    const int lpr = ln_lanes_per_row(C);
+    ln_train_bwd_kernel<<<ln_grid(rows, lpr, 4), LN_THREADS, (size_t)2 * C * 4, as_stream(stream)>>>(d_x, d_grad_y, grad_dtype == ICM_OUT_BF16, d_gamma, d_mean, d_rstd,
+                                                                                                        d_grad_x, d_grad_gamma, d_grad_beta, rows, C, lpr);
+    ICM_LAUNCH_CHECK();
+    return ICM_OK;
+}

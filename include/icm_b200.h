@@ -314,6 +314,15 @@ int icm_clip_coef(const float *d_sumsq, float max_norm, float pre_scale, float *
 int icm_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int step, float *d_step_state, const float *d_grad_scale, float grad_scale, void *stream);
 
+/* nn.LayerNorm (eps 1e-5) of the Swin blocks in the training step (stf.py:155,197,232,256,379): forward keeps the per-row mean and
+ * 1/std; y fp32 or bf16 (ICM_OUT_*).  Backward: grad_x, and grad_gamma / grad_beta summed over the rows (zeroed here first); grad_y fp32
+ * or bf16.  x is [rows, C] fp32 contiguous, C a multiple of 4, <= 768. */
+int icm_layernorm_train_forward(const float *d_x, const float *d_gamma, const float *d_beta, void *d_y, int y_dtype, float *d_mean,
+                                float *d_rstd, int64_t rows, int C, void *stream);
+int icm_layernorm_train_backward(const float *d_x, const void *d_grad_y, int grad_dtype, const float *d_gamma, const float *d_mean,
+                                 const float *d_rstd, float *d_grad_x, float *d_grad_gamma, float *d_grad_beta, int64_t rows, int C,
+                                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

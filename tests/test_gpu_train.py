@@ -74,6 +74,34 @@ def test_fused_gaussian_stage_matches_the_reference_expressions():
     assert torch.equal(a[4] == 0, b[4] == 0) or ((a[4] == 0) ^ (b[4] == 0)).float().mean() < 1e-3  # same pass-through pattern
 
 
+@pytest.mark.parametrize("C,rows", [(48, 1000), (96, 777), (192, 513), (384, 130), (768, 67)])
+def test_fused_layernorm_forward_and_backward_match_torch(C, rows):
+    """icm_layernorm_train_forward / backward vs F.layer_norm under autograd (fp32 and bf16 output / incoming gradient)."""
+    import torch.nn.functional as F
+
+    from compressai.models._train import _LayerNormTrain
+
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = (torch.randn(rows, C, device="cuda", generator=g) * 3 + 1).requires_grad_()
+    w = (1 + 0.2 * torch.randn(C, device="cuda", generator=g)).requires_grad_()
+    b = (0.2 * torch.randn(C, device="cuda", generator=g)).requires_grad_()
+    up = torch.randn(rows, C, device="cuda", generator=g)
+    ref = F.layer_norm(x, (C,), w, b)
+    ref.backward(up)
+    want = (ref.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone())
+    for bf16 in (False, True):
+        x.grad = w.grad = b.grad = None
+        y = _LayerNormTrain.apply(x, w, b, bf16)
+        assert y.dtype == (torch.bfloat16 if bf16 else torch.float32)
+        y.backward(up.to(y.dtype))
+        tol = 2e-2 if bf16 else 2e-5
+        assert torch.allclose(y.float(), want[0], rtol=tol, atol=tol)
+        gt = 2e-2 if bf16 else 1e-4   # a bf16 incoming gradient carries 8 mantissa bits
+        assert torch.allclose(x.grad, want[1], rtol=gt, atol=gt * float(want[1].abs().max()))
+        assert torch.allclose(w.grad, want[2], rtol=gt, atol=gt * float(want[2].abs().max()))
+        assert torch.allclose(b.grad, want[3], rtol=gt, atol=gt * float(want[3].abs().max()))
+
+
 def test_flat_adam_and_clipping_match_torch():
     """FlatAdam (icm_grad_sumsq + icm_clip_coef + icm_adam_step) vs torch.optim.Adam + clip_grad_norm_ over three steps,
     with a pre-scale as after a SUM all-reduce over 4 ranks."""
@@ -162,8 +190,14 @@ def test_fused_and_unfused_training_forward_agree():
         torch.manual_seed(77)
         o = m(x)
         outs.append(o)
-    assert torch.allclose(outs[0]["likelihoods"]["y"], outs[1]["likelihoods"]["y"], rtol=1e-3, atol=1e-12)
-    assert torch.allclose(outs[0]["x_hat"], outs[1]["x_hat"], rtol=1e-4, atol=1e-5)
+    # the fused LayerNorm differs from torch's by fp32 rounding (~1e-6); after 12 blocks a few y values sit on the other side of a
+    # rounding boundary, so y_hat (and with it a patch of x_hat, and that element's likelihood) may differ for a handful of
+    # elements: compare the bulk
+    ly0, ly1 = outs[0]["likelihoods"]["y"], outs[1]["likelihoods"]["y"]
+    close = (ly0 - ly1).abs() <= 1e-3 * ly1.abs() + 1e-12
+    assert float(close.float().mean()) >= 0.995
+    d = (outs[0]["x_hat"] - outs[1]["x_hat"]).abs()
+    assert float(d.mean()) <= 2e-4 and float((d > 5e-3).float().mean()) <= 0.01, (float(d.mean()), float(d.max()))
 
 
 def test_eval_forward_still_runs_the_inference_kernels_after_training_steps():
