@@ -90,15 +90,23 @@ def _bucket_worker(rank, world, port, q):
         flat = torch.zeros(off)
         for p, o, n in order:
             p.grad = flat[o:o + n].view_as(p)
-        gb = GradientBuckets(flat, order, bucket_bytes=1024)
+        import copy
+
+        twin = copy.deepcopy(net)  # same weights, no hooks: this rank's own gradients (the bucketed buffer is reduced in place,
+        gb = GradientBuckets(flat, order, bucket_bytes=1024)  # possibly while backward is still running)
         assert len(gb.buckets) >= 2 and gb.buckets[0][0] == 0 and gb.buckets[-1][1] == off
         results = []
         for step in range(2):  # twice: the arrival counters must re-arm
             flat.zero_()
             g = torch.Generator().manual_seed(100 * step + rank)
             x = torch.randn(8, 16, generator=g)
+            own = torch.autograd.grad(twin(x).square().sum(), list(twin.parameters()))
+            local = torch.zeros_like(flat)
+            by_param = dict(zip(net.parameters(), own))
+            for p, o, n in order:
+                if p in by_param:
+                    local[o:o + n] = by_param[p].reshape(-1)
             net(x).square().sum().backward()
-            local = flat.clone()
             gb.finish()
             results.append((local, flat.clone()))
         gb.remove()
