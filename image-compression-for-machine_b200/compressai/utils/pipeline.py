@@ -244,7 +244,14 @@ class RoundTripPipeline:
                 key = (slot, hi - lo, tuple(x.shape[1:]))
                 jg = self._job_graphs.get(key)
                 if jg is None and self._eager_runs.get(key, 0) >= 1 and self._may_capture():
-                    jg = self._job_graphs[key] = self._capture_job(slot, hi - lo, (hi - lo,) + tuple(x.shape[1:]))
+                    try:
+                        jg = self._job_graphs[key] = self._capture_job(slot, hi - lo, (hi - lo,) + tuple(x.shape[1:]))
+                    except RuntimeError as e:  # e.g. out of memory inside the capture: keep serving, eagerly
+                        warnings.warn(f"RoundTripPipeline: CUDA-graph capture failed ({str(e)[:120]}); continuing without graphs")
+                        self.cuda_graphs = False
+                        self._job_graphs = {}
+                        torch.cuda.synchronize()
+                        jg = None
                 if jg is not None:
                     return front_graph(t, jg)
                 self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
