@@ -18,6 +18,8 @@
 // sides of the codec see bit-identical means/scales (SURVEY.md §7 "Encoder/decoder determinism").
 #include "umma.cuh"
 
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <utility>
@@ -43,6 +45,7 @@ struct ConvParams {
     const void *residual;
     void *out;
     int *sched;              // {next tile to hand out beyond the first wave, CTAs finished}: this stream's tile counter
+    int dyn_first;           // the first tile of a CTA also comes from the counter
     // grouped launch (icm_conv2d_grouped): G convolutions of one geometry, tile id = g * tiles_per_group + tile in group
     int groups, tiles_per_group;
     unsigned long long fd_g;
@@ -89,8 +92,7 @@ constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter
 constexpr int TQ = 4;                              // depth of the tile-id queue between the scheduler thread and its consumers
 constexpr int CONV_THREADS = (2 + EPI_WARPS) * 32; // TMA warp + MMA warp + epilogue warps
 
-// Persistent with a DYNAMIC tile scheduler: a CTA's first tile is blockIdx.x, every further tile comes from an atomic
-// counter (gridDim.x + atomicAdd).  The TMA thread is the scheduler: it fetches the tile id one tile ahead and hands
+// Persistent with a DYNAMIC tile scheduler: every tile of a CTA, the first included, comes from an atomic counter.  The TMA thread is the scheduler: it fetches the tile id one tile ahead and hands
 // it to the MMA thread and the epilogue warps through a small mbarrier-guarded queue in shared memory.  A CTA that
 // starts late -- its SM was held by an rANS coder CTA of another stream, which cannot share an SM with this kernel's
 // ~200 KB of shared memory -- therefore finds no work left instead of delaying the launch by the tiles a static
@@ -165,7 +167,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            int tile = blockIdx.x; // < total_tiles: the grid never exceeds the number of tiles
+            // first tile: blockIdx.x, or (dyn_first) drawn from the counter like every later one, so that a CTA that starts late
+            // -- its SM was held by a coder CTA of another stream -- owns no tile at all and leaves at once
+            int tile = p.dyn_first ? atomicAdd(p.sched, 1) : (int)blockIdx.x;
             int slot = 0;
             uint32_t qphase = 0;
             while (true) {
@@ -174,7 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mbar_arrive(&tq_full[slot]); // release semantics: the id is visible to whoever observes the phase
                 if (++slot == TQ) { slot = 0; qphase ^= 1; }
                 if (tile >= p.total_tiles) break;
-                const int next = (int)gridDim.x + atomicAdd(p.sched, 1); // in flight while this tile's loads are issued
+                const int next = (p.dyn_first ? 0 : (int)gridDim.x) + atomicAdd(p.sched, 1); // in flight while this tile's loads are issued
                 int n0, w0, h0, b, g;
                 tile_coords(tile, n0, w0, h0, b, g);
                 tile = next;
@@ -609,6 +613,8 @@ static int launch_conv(const icm_conv_args *a, const icm_conv_groups *grp, void 
     p.fd_g = G > 1 ? magic(p.tiles_per_group) : 0;
     p.sched = tile_counter(as_stream(stream));
     if (!p.sched) return ICM_ERR_CUDA;
+    static const bool dyn_first = getenv("ICM_CONV_STATIC_FIRST") == nullptr; // A/B switch
+    p.dyn_first = dyn_first ? 1 : 0;
     const int max_ctas = persistent_grid_limit();
     const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
     conv_igemm_kernel<<<grid, CONV_THREADS, smem_bytes, as_stream(stream)>>>(map_a, map_w, p);
