@@ -23,6 +23,8 @@
 // window_attention_kernel (transforms.cu).  A window reads and writes only its own 16 tokens, so x is updated in place.
 // Results are deterministic and batch-invariant (fixed reduction order per window), which is all the codec needs:
 // encoder and decoder run the same kernel.
+#include <stdlib.h>
+
 #include "mma_sync.cuh"
 #include "umma.cuh"
 
@@ -61,6 +63,8 @@ struct Params {
     const __nv_bfloat16 *w_qkv, *w_proj, *w_fc1, *w_fc2; // [N][ld] bf16 rows (icm_pack_conv_weight layout for 1x1: ld = Cin padded to 64)
     int ld_c, ld_h;                                      // row pitch of the K = C and K = 4C weights
     const float *ln1_g, *ln1_b, *b_qkv, *b_proj, *rel_table, *ln2_g, *ln2_b, *b_fc1, *b_fc2;
+    int *sched; // {next window to hand out, CTAs finished}: the stream's scheduling counter pair (csrc/conv.cu tile_counter)
+    int dynamic; // 0: static grid-stride walk (A/B switch ICM_SWIN_STATIC)
 };
 
 // feature held by accumulator column (2tq + e) of n-tile nt.  The weight row for column g of n-tile nt is feature
@@ -193,7 +197,19 @@ __global__ void __launch_bounds__(256) swin_block_kernel(const Params p)
             const int i = g + 8 * r, j = (c >> 1) * 8 + 2 * tq + (c & 1);
             rel[r][c] = L::o_rel + (((i >> 2) - (j >> 2) + WIN - 1) * (2 * WIN - 1) + ((i & 3) - (j & 3) + WIN - 1)) * heads;
         }
-    for (long long win = (long long)blockIdx.x * warps + warp; win < n_win; win += (long long)gridDim.x * warps) {
+    // Windows are handed out dynamically, one per warp at a time, from a counter in global memory (the next index is fetched while
+    // the current window is processed).  A static grid-stride walk reserves a fixed share of the windows for every CTA, and in
+    // the serving pipeline a CTA whose SM is held by an rANS decoder CTA of another stream (~190 KB of shared memory, 5 ms per
+    // step) starts only when another CTA of this launch has finished -- the launch then takes twice as long.
+    int nxt = (int)blockIdx.x * warps + warp;
+    if (p.dynamic) {
+        if (lane == 0) nxt = atomicAdd(p.sched, 1);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    while (nxt < n_win) {
+        const long long win = nxt;
+        if (!p.dynamic) nxt += (int)gridDim.x * warps;
+        else if (lane == 0) nxt = atomicAdd(p.sched, 1); // in flight while this window is processed
         long long t = win;
         const int ww = (int)(t % nWw); t /= nWw;
         const int wh = (int)(t % nWh);
@@ -331,7 +347,10 @@ __global__ void __launch_bounds__(256) swin_block_kernel(const Params p)
         }
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) { pa[4 * kt] = xa[kt]; pb[4 * kt] = xb[kt]; }
+        if (p.dynamic) nxt = __shfl_sync(0xffffffffu, nxt, 0);
     }
+    __syncthreads(); // every warp of this CTA has drawn its last index
+    if (p.dynamic && threadIdx.x == 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; } // last CTA re-arms the pair
 }
 
 template <int C, bool ATTN, bool MLP>
@@ -351,7 +370,12 @@ static int launch(const Params &p, cudaStream_t st)
     if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, L::bytes) != cudaSuccess || per_sm < 1)) per_sm = 1;
     const long long want = (n_win + warps - 1) / warps;
     const long long cap = (long long)persistent_grid_limit() * per_sm;
-    kernel<<<(unsigned)(want < cap ? want : cap), warps * 32, L::bytes, st>>>(p);
+    Params q = p;
+    q.sched = tile_counter(st);
+    if (!q.sched) return ICM_ERR_CUDA;
+    static const bool dyn = getenv("ICM_SWIN_STATIC") == nullptr;
+    q.dynamic = dyn ? 1 : 0;
+    kernel<<<(unsigned)(want < cap ? want : cap), warps * 32, L::bytes, st>>>(q);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
 }
