@@ -26,6 +26,8 @@
 //   rans_decode_warp_kernel   round-1 kernel (speculative 32-entry window + ballot search), the fallback for table
 //                             sets that do not fit the bucket image or contain a symbol of frequency 65535.
 #include "common.cuh"
+#include <string.h>
+
 #include "rans_lane.cuh"
 
 #include <stdlib.h>
@@ -201,13 +203,28 @@ __device__ __noinline__ EncState enc_escape(EncState st, uint32_t raw, uint32_t 
     return st;
 }
 
-__global__ void __launch_bounds__(32) rans_encode_kernel(const Record *__restrict__ rec, long long n_pad,
-                                                         uint32_t *__restrict__ words, long long cap_words,
-                                                         int32_t *__restrict__ sizes, const int32_t *__restrict__ status)
+// Up to 8 streams share a CTA (one warp each, nothing shared between them; ICM_ENC_WARPS overrides).  With one-warp CTAs the block
+// scheduler spread a job's 32 encoders over 32 SMs for ~37 ms, and on every one of them that warp's registers kept the second
+// swin_block CTA (2 x 32 768 registers fill the file) from being resident: the pipelined step lost ~4 ms to its encoders and only
+// 0.5 ms to its decoders (tools/ab_coders.sh: 860-878 images/s with 1 warp per CTA, 888-906 with 8, 924-933 without encoders).
+// Eight warps per CTA confine a job's encoders to 4 SMs; two warps per scheduler cost a stream ~12 % of its speed (38 -> 43 ms
+// with every CTA full; a lone stream, B = 1, is as fast as before).
+constexpr int kEncWarpsMax = 8;
+constexpr int kEncWarpBytes = 2 * 64 * 16 + kEncOutWords * 4; // 2 432
+
+__global__ void __launch_bounds__(32 * kEncWarpsMax, 1) rans_encode_kernel(const Record *__restrict__ rec, long long n_pad,
+                                                                        uint32_t *__restrict__ words, long long cap_words,
+                                                                        int32_t *__restrict__ sizes, const int32_t *__restrict__ status,
+                                                                        int n_streams)
 {
-    __shared__ __align__(16) uint4 s_rec[2][64]; // [buffer][symbol * 2 + half]
-    __shared__ uint32_t s_out[kEncOutWords];
-    const int s = blockIdx.x, lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char s_enc[]; // per warp: records [2][64] uint4 (buffer, symbol * 2 + half) + output words
+    // the warp index is broadcast with a shuffle so that the compiler sees warp-uniform control flow (with a plain threadIdx.x >> 5 it
+    // wraps the per-symbol branches in convergence barriers: 36.6 -> 41.4 ms per stream)
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (s >= n_streams) return; // whole warp
+    uint4 (*s_rec)[64] = reinterpret_cast<uint4 (*)[64]>(s_enc + (size_t)wid * kEncWarpBytes);
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_enc + (size_t)wid * kEncWarpBytes + 2 * 64 * sizeof(uint4));
     const uint4 *R = reinterpret_cast<const uint4 *>(rec + (size_t)s * n_pad);
     uint32_t *top = words + (size_t)(s + 1) * cap_words; // one past the last word of this stream's scratch
     const uint32_t rec_base = smem_addr(&s_rec[0][0]), out_base = smem_addr(&s_out[0]);
@@ -865,7 +882,8 @@ extern "C" int icm_rans_encode_batch(const icm_tables *t, const int32_t *d_symbo
     ICM_CHECK_ARG(((uintptr_t)d_packed & 3) == 0 && ((uintptr_t)d_work & 255) == 0, "icm_rans_encode_batch: misaligned buffers");
     ICM_CHECK_ARG(t->device == current_device(), "icm_rans_encode_batch: tables were created on device %d", t->device);
     cudaStream_t st = as_stream(stream);
-    static const bool skip = getenv("ICM_DEBUG_SKIP_CODERS") != nullptr; // profiling aid: what does the pipeline do without the coders?
+    // profiling aid: what does the pipeline do without the coders?  ICM_DEBUG_SKIP_CODERS=enc / dec skips one side only
+    static const bool skip = getenv("ICM_DEBUG_SKIP_CODERS") != nullptr && strcmp(getenv("ICM_DEBUG_SKIP_CODERS"), "dec") != 0;
     if (skip) { ICM_CUDA(cudaMemsetAsync(d_sizes, 0, (size_t)(n_streams + 1) * 4, st)); return ICM_OK; }
     const EncLayout L = enc_layout(n_streams, n_per_stream);
     char *w = (char *)d_work;
@@ -880,7 +898,8 @@ extern "C" int icm_rans_encode_batch(const icm_tables *t, const int32_t *d_symbo
         rans_records_kernel<<<grid, 256, 0, st>>>(t->dev, d_symbols, d_indexes, n_streams, n_per_stream, L.n_pad, rec, status);
         ICM_LAUNCH_CHECK();
     }
-    rans_encode_kernel<<<n_streams, 32, 0, st>>>(rec, L.n_pad, words, L.cap_words, d_sizes, status);
+    static const int enc_warps = [] { const char *e = getenv("ICM_ENC_WARPS"); const int v = e ? atoi(e) : kEncWarpsMax; return v >= 1 && v <= kEncWarpsMax ? v : kEncWarpsMax; }();
+    rans_encode_kernel<<<(n_streams + enc_warps - 1) / enc_warps, 32 * enc_warps, (size_t)enc_warps * kEncWarpBytes, st>>>(rec, L.n_pad, words, L.cap_words, d_sizes, status, n_streams);
     ICM_LAUNCH_CHECK();
     rans_scan_kernel<<<1, 32, 0, st>>>(d_sizes, n_streams, offs, d_sizes + n_streams);
     ICM_LAUNCH_CHECK();
@@ -986,7 +1005,7 @@ extern "C" int icm_rans_decoder_step(icm_rans_decoder *d, const icm_tables *t, c
     ICM_CHECK_ARG(t->device == dev && d->device == dev, "icm_rans_decoder_step: tables (device %d) / decoder (device %d) used on device %d",
                   t->device, d->device, dev);
     if (n_per_stream == 0) return ICM_OK;
-    static const bool skip = getenv("ICM_DEBUG_SKIP_CODERS") != nullptr;
+    static const bool skip = getenv("ICM_DEBUG_SKIP_CODERS") != nullptr && strcmp(getenv("ICM_DEBUG_SKIP_CODERS"), "enc") != 0;
     if (skip) { ICM_CUDA(cudaMemsetAsync(d_out, 0, (size_t)d->n_streams * n_per_stream * 4, as_stream(stream))); return ICM_OK; }
     const int S = d->n_streams;
     int warps = g_dec_warps;
