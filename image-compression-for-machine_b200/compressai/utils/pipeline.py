@@ -1,6 +1,6 @@
 """Stream-pipelined codec loop for throughput serving.
 
-The two rANS coders are latency-bound (one warp per image stream, ~35 ms to encode and ~60 ms to decode a
+The two rANS coders are latency-bound (one warp per image stream, ~37-44 ms to encode and ~48 ms to decode a
 768x512 image whatever the batch size) while the transforms are throughput-bound.  A batch is therefore cut
 into jobs of `part` images; each job runs compress -> decompress on one stream of a small pool, jobs of the
 same and of following batches are spread round-robin over the pool, and the GPU overlaps the coder of one
