@@ -53,7 +53,7 @@ class RoundTripPipeline:
         self.part = int(part)
         self.lag = max(0, min(int(lag), self.n_streams - 1))
         self.chains = max(0, int(chains))
-        # decode_priority: the latency-bound decode loop of a job (12 x {two conv stacks, a decoder step, a conv stack}, small
+        # decode_priority: the latency-bound decode loop of a job (7 x {grouped conv stacks, a decoder step, a grouped conv stack}, small
         # kernels) runs on a high-priority twin of the job's stream, so that its CTAs are placed ahead of the queued CTAs of
         # other jobs' throughput-bound kernels
         self.decode_priority = bool(decode_priority)
