@@ -184,17 +184,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tile = next;
                 const int img = b + p.a_img[g], wrow = n0 + g * p.w_group_rows;
                 const int tail_c = p.has_tail ? p.tail_ch[g] : (p.k_chunks - 1) * BK;
+                // (tap, chunk) -> (dy, dx, channel, weight column) advance by counters: this one thread issues every load of the
+                // CTA, and the two runtime integer divisions a k-step used to start with (it / k_chunks, tap / KW: ~25 dependent
+                // instructions each, ~5 cycles apiece in a lone thread) made the k-step period ~400-500 cycles whatever N --
+                // longer than the four MMAs of a k-step take for N <= 176 (tools/umma_issue_bench.cu: 40 / 48 / 64 / 96 cycles
+                // per MMA at N = 32 / 64 / 128 / 192), so those layers were bound by this loop, not by the tensor pipe.
+                const int wx0 = w0 * p.stride - p.pad, hy0 = h0 * p.stride - p.pad, last_chunk = p.k_chunks - 1;
+                int chunk = 0, dx = 0, dy = 0, wcol = 0, ch = 0;
                 for (int it = 0; it < k_iters; ++it) {
-                    const int tap = it / p.k_chunks, chunk = it - tap * p.k_chunks;
-                    const int dy = tap / p.KW, dx = tap - dy * p.KW;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = tiles + (size_t)stage * stage_bytes;
                     unsigned char *sb = sa + a_bytes;
                     mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-                    tma_load_4d(&map_a, &full_bar[stage], sa, chunk == p.k_chunks - 1 ? tail_c : chunk * BK, w0 * p.stride + dx - p.pad,
-                                h0 * p.stride + dy - p.pad, img);
-                    tma_load_2d(&map_w, &full_bar[stage], sb, tap * p.Cin_pad + chunk * BK, wrow);
+                    tma_load_4d(&map_a, &full_bar[stage], sa, chunk == last_chunk ? tail_c : ch, wx0 + dx, hy0 + dy, img);
+                    tma_load_2d(&map_w, &full_bar[stage], sb, wcol + ch, wrow);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    ch += BK;
+                    if (++chunk == p.k_chunks) { // next tap
+                        chunk = 0; ch = 0; wcol += p.Cin_pad;
+                        if (++dx == p.KW) { dx = 0; ++dy; }
+                    }
                 }
             }
         }

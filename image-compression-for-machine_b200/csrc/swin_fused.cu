@@ -113,21 +113,24 @@ __device__ __forceinline__ void layernorm_frag(const float4 (&xa)[C / 16], const
     }
 }
 
-// acc (one n-tile pair = 16 output features starting at n-tile 2*j) = bias + A[16 x K] * W[rows of the pair][K]^T
-template <int KT>
-__device__ __forceinline__ void gemm_pair(float (&acc)[2][4], const uint32_t (&af)[KT][4], const __nv_bfloat16 *w, int stride, int j,
+// acc[w] (one n-tile pair = 16 output features starting at n-tile 2*j) = bias + A_w[16 x K] * W[rows of the pair][K]^T for the
+// warp's NW windows: every weight fragment is loaded from shared memory once and used NW times
+template <int KT, int NW>
+__device__ __forceinline__ void gemm_pair(float (&acc)[NW][2][4], const uint32_t (&af)[NW][KT][4], const __nv_bfloat16 *w, int stride, int j,
                                           const float *bias, int g, int tq)
 {
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int nt = 2 * j + p;
         const float2 b = *reinterpret_cast<const float2 *>(bias + feat(nt, tq, 0));
-        acc[p][0] = b.x; acc[p][1] = b.y; acc[p][2] = b.x; acc[p][3] = b.y;
+#pragma unroll
+        for (int w_ = 0; w_ < NW; ++w_) { acc[w_][p][0] = b.x; acc[w_][p][1] = b.y; acc[w_][p][2] = b.x; acc[w_][p][3] = b.y; }
         const __nv_bfloat16 *wr = w + (size_t)wrow(nt, g) * stride + 4 * tq;
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
             const uint2 bf = lds64(wr + kt * 16);
-            mma_bf16_16816(acc[p], af[kt], bf.x, bf.y);
+#pragma unroll
+            for (int w_ = 0; w_ < NW; ++w_) mma_bf16_16816(acc[w_][p], af[w_][kt], bf.x, bf.y);
         }
     }
 }
@@ -146,8 +149,15 @@ __device__ __forceinline__ float gelu_tanh(float v)
     return fmaf(hv, t, hv);
 }
 
-template <int C, bool ATTN, bool MLP>
-__global__ void __launch_bounds__(256) swin_block_kernel(const Params p)
+// WARPS warps per CTA (MINB CTAs per SM), NW windows per warp at a time.  Measured on B200, 64 images (tools/swin_shape_ab.py; every
+// shape gives the same bits):
+//   C = 48: 8 warps x 2 CTAs, NW = 1: 1.52 ms per block; 10 / 12 warps x 2 CTAs (96 / 80 registers, spills): 1.54 / 1.62;
+//           NW = 2 (every weight fragment feeds two windows' MMAs: half the shared-memory traffic, 225 registers, one CTA):
+//           1.89 with 8 warps, 1.72 with 12 -- the kernel is bound by its dependent-issue chains, not by the LSU pipe;
+//   C = 96: one window takes 170-190 registers, one CTA per SM: 8 / 12 / 14 / 16 warps: 1.46 / 1.31-1.34 / 1.67 / 1.62 ms
+//           (attention + MLP passes; 12 warps cap the kernel at 168 registers with 30-70 bytes of spills, 14 and 16 at 128).
+template <int C, bool ATTN, bool MLP, int WARPS, int NW, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) swin_block_kernel(const Params p)
 {
     using L = Layout<C, ATTN, MLP>;
     constexpr int KT = C / 16, NT = C / 8, heads = C / HD;
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(256) swin_block_kernel(const Params p)
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, tq = lane & 3;
     const int H = p.H, W = p.W, shift = p.shift;
     const int nWw = W / WIN, nWh = H / WIN;
@@ -197,187 +207,235 @@ __global__ void __launch_bounds__(256) swin_block_kernel(const Params p)
             const int i = g + 8 * r, j = (c >> 1) * 8 + 2 * tq + (c & 1);
             rel[r][c] = L::o_rel + (((i >> 2) - (j >> 2) + WIN - 1) * (2 * WIN - 1) + ((i & 3) - (j & 3) + WIN - 1)) * heads;
         }
-    // Windows are handed out dynamically, one per warp at a time, from a counter in global memory (the next index is fetched while
-    // the current window is processed).  A static grid-stride walk reserves a fixed share of the windows for every CTA, and in
+    // Windows are handed out dynamically, NW per warp at a time, from a counter in global memory (the next index is fetched while
+    // the current windows are processed).  A static grid-stride walk reserves a fixed share of the windows for every CTA, and in
     // the serving pipeline a CTA whose SM is held by an rANS decoder CTA of another stream (~190 KB of shared memory, 5 ms per
     // step) starts only when another CTA of this launch has finished -- the launch then takes twice as long.
-    int nxt = (int)blockIdx.x * warps + warp;
+    int nxt = ((int)blockIdx.x * WARPS + warp) * NW;
     if (p.dynamic) {
-        if (lane == 0) nxt = atomicAdd(p.sched, 1);
+        if (lane == 0) nxt = atomicAdd(p.sched, NW);
         nxt = __shfl_sync(0xffffffffu, nxt, 0);
     }
     while (nxt < n_win) {
-        const long long win = nxt;
-        if (!p.dynamic) nxt += (int)gridDim.x * warps;
-        else if (lane == 0) nxt = atomicAdd(p.sched, 1); // in flight while this window is processed
-        long long t = win;
-        const int ww = (int)(t % nWw); t /= nWw;
-        const int wh = (int)(t % nWh);
-        const int b = (int)(t / nWh);
-        // the two window tokens whose rows this lane holds (g and g + 8), in the shifted and the original grid
-        long long tokA, tokB;
-        int labA = 0, labB = 0;
-        auto locate = [&](int tok, long long &token, int &label) {
-            const int hs = wh * WIN + (tok >> 2), ws = ww * WIN + (tok & 3);
-            int h = hs + shift, w = ws + shift;
-            if (h >= H) h -= H;
-            if (w >= W) w -= W;
-            token = ((long long)b * H + h) * W + w;
-            if (shift > 0) label = 3 * (hs < H - WIN ? 0 : (hs < H - shift ? 1 : 2)) + (ws < W - WIN ? 0 : (ws < W - shift ? 1 : 2));
-        };
-        locate(g, tokA, labA);
-        locate(g + 8, tokB, labB);
-        // SW-MSA mask of this lane's score elements, one bit each: query and key in different regions (stf.py:316-334);
-        // a property of the window, not of the head
-        uint32_t masked = 0;
-        if (ATTN && shift > 0) {
+        const long long win0 = nxt;
+        if (!p.dynamic) nxt += (int)gridDim.x * WARPS * NW;
+        else if (lane == 0) nxt = atomicAdd(p.sched, NW); // in flight while these windows are processed
+        float4 *pa[NW], *pb[NW];
+        float4 xa[NW][KT], xb[NW][KT];
+        uint32_t masked[NW];
+        bool live[NW];
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+        for (int w = 0; w < NW; ++w) {
+            // an odd tail: the surplus slot recomputes window win0 (loaded before anything is stored) and stores nothing
+            live[w] = win0 + w < n_win;
+            long long t = live[w] ? win0 + w : win0;
+            const int ww = (int)(t % nWw); t /= nWw;
+            const int wh = (int)(t % nWh);
+            const int b = (int)(t / nWh);
+            // the two window tokens whose rows this lane holds (g and g + 8), in the shifted and the original grid
+            long long tokA, tokB;
+            int labA = 0, labB = 0;
+            auto locate = [&](int tok, long long &token, int &label) {
+                const int hs = wh * WIN + (tok >> 2), ws = ww * WIN + (tok & 3);
+                int h = hs + shift, w2 = ws + shift;
+                if (h >= H) h -= H;
+                if (w2 >= W) w2 -= W;
+                token = ((long long)b * H + h) * W + w2;
+                if (shift > 0) label = 3 * (hs < H - WIN ? 0 : (hs < H - shift ? 1 : 2)) + (ws < W - WIN ? 0 : (ws < W - shift ? 1 : 2));
+            };
+            locate(g, tokA, labA);
+            locate(g + 8, tokB, labB);
+            // SW-MSA mask of this lane's score elements, one bit each: query and key in different regions (stf.py:316-334);
+            // a property of the window, not of the head
+            masked[w] = 0;
+            if (ATTN && shift > 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int j = (c >> 1) * 8 + 2 * tq + (c & 1);
-                    const int hj = wh * WIN + (j >> 2), wj = ww * WIN + (j & 3);
-                    const int lj = 3 * (hj < H - WIN ? 0 : (hj < H - shift ? 1 : 2)) + (wj < W - WIN ? 0 : (wj < W - shift ? 1 : 2));
-                    if (lj != (r ? labB : labA)) masked |= 1u << (r * 4 + c);
-                }
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int j = (c >> 1) * 8 + 2 * tq + (c & 1);
+                        const int hj = wh * WIN + (j >> 2), wj = ww * WIN + (j & 3);
+                        const int lj = 3 * (hj < H - WIN ? 0 : (hj < H - shift ? 1 : 2)) + (wj < W - WIN ? 0 : (wj < W - shift ? 1 : 2));
+                        if (lj != (r ? labB : labA)) masked[w] |= 1u << (r * 4 + c);
+                    }
+            }
+            pa[w] = reinterpret_cast<float4 *>(p.x + tokA * C) + tq;
+            pb[w] = reinterpret_cast<float4 *>(p.x + tokB * C) + tq;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) { xa[w][kt] = pa[w][4 * kt]; xb[w][kt] = pb[w][4 * kt]; }
         }
-        float4 *pa = reinterpret_cast<float4 *>(p.x + tokA * C) + tq, *pb = reinterpret_cast<float4 *>(p.x + tokB * C) + tq;
-        float4 xa[KT], xb[KT];
-#pragma unroll
-        for (int kt = 0; kt < KT; ++kt) { xa[kt] = pa[4 * kt]; xb[kt] = pb[4 * kt]; }
 
         if (ATTN) {
-            uint32_t af[KT][4];
-            layernorm_frag<C>(xa, xb, s_f + L::o_ln1, tq, af);
-            float po[NT][4]; // proj accumulators
+            uint32_t af[NW][KT][4];
+            float po[NW][NT][4]; // proj accumulators
+#pragma unroll
+            for (int w = 0; w < NW; ++w) layernorm_frag<C>(xa[w], xb[w], s_f + L::o_ln1, tq, af[w]);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const float2 bb = *reinterpret_cast<const float2 *>(s_f + L::o_bproj + feat(nt, tq, 0));
-                po[nt][0] = bb.x; po[nt][1] = bb.y; po[nt][2] = bb.x; po[nt][3] = bb.y;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { po[w][nt][0] = bb.x; po[w][nt][1] = bb.y; po[w][nt][2] = bb.x; po[w][nt][3] = bb.y; }
             }
 #pragma unroll 1
             for (int head = 0; head < heads; ++head) {
-                float q[2][4], k[2][4], v[2][4];
-                gemm_pair<KT>(q, af, s_qkv, L::S_C, head, s_f + L::o_bqkv, g, tq);
-                gemm_pair<KT>(k, af, s_qkv, L::S_C, heads + head, s_f + L::o_bqkv, g, tq);
-                gemm_pair<KT>(v, af, s_qkv, L::S_C, 2 * heads + head, s_f + L::o_bqkv, g, tq);
-                // S = q k^T: q's accumulators are the A fragment, k's the B fragments (keys 0..7 from rows g, keys 8..15 from rows g+8)
-                uint32_t qa[4];
-                qa[0] = pack_bf16(q[0][0], q[0][1]); qa[1] = pack_bf16(q[0][2], q[0][3]);
-                qa[2] = pack_bf16(q[1][0], q[1][1]); qa[3] = pack_bf16(q[1][2], q[1][3]);
-                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16_16816(s0, qa, pack_bf16(k[0][0], k[0][1]), pack_bf16(k[1][0], k[1][1]));
-                mma_bf16_16816(s1, qa, pack_bf16(k[0][2], k[0][3]), pack_bf16(k[1][2], k[1][3]));
-                float sc[2][4]; // [row g / g+8][key slot: 2tq, 2tq+1, 8+2tq, 9+2tq]
-                sc[0][0] = s0[0]; sc[0][1] = s0[1]; sc[0][2] = s1[0]; sc[0][3] = s1[1];
-                sc[1][0] = s0[2]; sc[1][1] = s0[3]; sc[1][2] = s1[2]; sc[1][3] = s1[3];
+                float q[NW][2][4], k[NW][2][4], v[NW][2][4];
+                gemm_pair<KT, NW>(q, af, s_qkv, L::S_C, head, s_f + L::o_bqkv, g, tq);
+                gemm_pair<KT, NW>(k, af, s_qkv, L::S_C, heads + head, s_f + L::o_bqkv, g, tq);
+                gemm_pair<KT, NW>(v, af, s_qkv, L::S_C, 2 * heads + head, s_f + L::o_bqkv, g, tq);
+                float relb[2][4]; // B[rel] of this head: the same for every window
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    float mx = -1e30f;
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        // q k^T * head_dim ** -0.5 (stf.py:63,100) + B[rel] (+ mask: -100, stf.py:334)
-                        float a = fmaf(sc[r][c], 0.25f, s_f[rel[r][c] + head]);
-                        if (masked & (1u << (r * 4 + c))) a += -100.0f;
-                        sc[r][c] = a;
-                        mx = fmaxf(mx, a);
+                    for (int c = 0; c < 4; ++c) relb[r][c] = s_f[rel[r][c] + head];
+                uint32_t oa[NW][4];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    // S = q k^T: q's accumulators are the A fragment, k's the B fragments (keys 0..7 from rows g, keys 8..15 from rows g+8)
+                    uint32_t qa[4];
+                    qa[0] = pack_bf16(q[w][0][0], q[w][0][1]); qa[1] = pack_bf16(q[w][0][2], q[w][0][3]);
+                    qa[2] = pack_bf16(q[w][1][0], q[w][1][1]); qa[3] = pack_bf16(q[w][1][2], q[w][1][3]);
+                    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_bf16_16816(s0, qa, pack_bf16(k[w][0][0], k[w][0][1]), pack_bf16(k[w][1][0], k[w][1][1]));
+                    mma_bf16_16816(s1, qa, pack_bf16(k[w][0][2], k[w][0][3]), pack_bf16(k[w][1][2], k[w][1][3]));
+                    float sc[2][4]; // [row g / g+8][key slot: 2tq, 2tq+1, 8+2tq, 9+2tq]
+                    sc[0][0] = s0[0]; sc[0][1] = s0[1]; sc[0][2] = s1[0]; sc[0][3] = s1[1];
+                    sc[1][0] = s0[2]; sc[1][1] = s0[3]; sc[1][2] = s1[2]; sc[1][3] = s1[3];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        float mx = -1e30f;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            // q k^T * head_dim ** -0.5 (stf.py:63,100) + B[rel] (+ mask: -100, stf.py:334)
+                            float a = fmaf(sc[r][c], 0.25f, relb[r][c]);
+                            if (masked[w] & (1u << (r * 4 + c))) a += -100.0f;
+                            sc[r][c] = a;
+                            mx = fmaxf(mx, a);
+                        }
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                        float den = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { sc[r][c] = __expf(sc[r][c] - mx); den += sc[r][c]; }
+                        den += __shfl_xor_sync(0xffffffffu, den, 1);
+                        den += __shfl_xor_sync(0xffffffffu, den, 2);
+                        const float inv = 1.0f / den;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) sc[r][c] *= inv;
                     }
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                    float den = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) { sc[r][c] = __expf(sc[r][c] - mx); den += sc[r][c]; }
-                    den += __shfl_xor_sync(0xffffffffu, den, 1);
-                    den += __shfl_xor_sync(0xffffffffu, den, 2);
-                    const float inv = 1.0f / den;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) sc[r][c] *= inv;
+                    uint32_t pf[4]; // P as the A fragment of O = P V
+                    pf[0] = pack_bf16(sc[0][0], sc[0][1]); pf[1] = pack_bf16(sc[1][0], sc[1][1]);
+                    pf[2] = pack_bf16(sc[0][2], sc[0][3]); pf[3] = pack_bf16(sc[1][2], sc[1][3]);
+                    // V's accumulators hold V[token g / g+8][d]; the B fragment wants V[token 2tq..][d = g]: transposed 8x8 blocks
+                    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_bf16_16816(o0, pf, movmatrix_trans(pack_bf16(v[w][0][0], v[w][0][1])), movmatrix_trans(pack_bf16(v[w][0][2], v[w][0][3])));
+                    mma_bf16_16816(o1, pf, movmatrix_trans(pack_bf16(v[w][1][0], v[w][1][1])), movmatrix_trans(pack_bf16(v[w][1][2], v[w][1][3])));
+                    // the head's output is k-group `head` of proj's input
+                    oa[w][0] = pack_bf16(o0[0], o0[1]); oa[w][1] = pack_bf16(o0[2], o0[3]);
+                    oa[w][2] = pack_bf16(o1[0], o1[1]); oa[w][3] = pack_bf16(o1[2], o1[3]);
                 }
-                uint32_t pf[4]; // P as the A fragment of O = P V
-                pf[0] = pack_bf16(sc[0][0], sc[0][1]); pf[1] = pack_bf16(sc[1][0], sc[1][1]);
-                pf[2] = pack_bf16(sc[0][2], sc[0][3]); pf[3] = pack_bf16(sc[1][2], sc[1][3]);
-                // V's accumulators hold V[token g / g+8][d]; the B fragment wants V[token 2tq..][d = g]: transposed 8x8 blocks
-                float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16_16816(o0, pf, movmatrix_trans(pack_bf16(v[0][0], v[0][1])), movmatrix_trans(pack_bf16(v[0][2], v[0][3])));
-                mma_bf16_16816(o1, pf, movmatrix_trans(pack_bf16(v[1][0], v[1][1])), movmatrix_trans(pack_bf16(v[1][2], v[1][3])));
-                // the head's output is k-group `head` of proj's input
-                uint32_t oa[4];
-                oa[0] = pack_bf16(o0[0], o0[1]); oa[1] = pack_bf16(o0[2], o0[3]);
-                oa[2] = pack_bf16(o1[0], o1[1]); oa[3] = pack_bf16(o1[2], o1[3]);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const uint2 bf = lds64(s_proj + (size_t)wrow(nt, g) * L::S_C + head * 16 + 4 * tq);
-                    mma_bf16_16816(po[nt], oa, bf.x, bf.y);
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) mma_bf16_16816(po[w][nt], oa[w], bf.x, bf.y);
                 }
             }
             // residual: accumulator column (2tq + e) of n-tile 2kt + h2 is channel kt*16 + 4tq + 2*h2 + e = the x registers
 #pragma unroll
-            for (int kt = 0; kt < KT; ++kt) {
-                xa[kt].x += po[2 * kt][0]; xa[kt].y += po[2 * kt][1]; xa[kt].z += po[2 * kt + 1][0]; xa[kt].w += po[2 * kt + 1][1];
-                xb[kt].x += po[2 * kt][2]; xb[kt].y += po[2 * kt][3]; xb[kt].z += po[2 * kt + 1][2]; xb[kt].w += po[2 * kt + 1][3];
-            }
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    xa[w][kt].x += po[w][2 * kt][0]; xa[w][kt].y += po[w][2 * kt][1]; xa[w][kt].z += po[w][2 * kt + 1][0]; xa[w][kt].w += po[w][2 * kt + 1][1];
+                    xb[w][kt].x += po[w][2 * kt][2]; xb[w][kt].y += po[w][2 * kt][3]; xb[w][kt].z += po[w][2 * kt + 1][2]; xb[w][kt].w += po[w][2 * kt + 1][3];
+                }
         }
         if (MLP) {
-            uint32_t af[KT][4];
-            layernorm_frag<C>(xa, xb, s_f + L::o_ln2, tq, af);
-            float mo[NT][4]; // fc2 accumulators
+            uint32_t af[NW][KT][4];
+            float mo[NW][NT][4]; // fc2 accumulators
+#pragma unroll
+            for (int w = 0; w < NW; ++w) layernorm_frag<C>(xa[w], xb[w], s_f + L::o_ln2, tq, af[w]);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const float2 bb = *reinterpret_cast<const float2 *>(s_f + L::o_b2 + feat(nt, tq, 0));
-                mo[nt][0] = bb.x; mo[nt][1] = bb.y; mo[nt][2] = bb.x; mo[nt][3] = bb.y;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { mo[w][nt][0] = bb.x; mo[w][nt][1] = bb.y; mo[w][nt][2] = bb.x; mo[w][nt][3] = bb.y; }
             }
-#pragma unroll 2
+#pragma unroll(NW == 1 ? 2 : 1)
             for (int j = 0; j < 4 * C / 16; ++j) { // 16 hidden features at a time
-                float h[2][4];
-                gemm_pair<KT>(h, af, s_fc1, L::S_C, j, s_f + L::o_b1, g, tq);
-                uint32_t ha[4];
-                ha[0] = pack_bf16(gelu_tanh(h[0][0]), gelu_tanh(h[0][1])); ha[1] = pack_bf16(gelu_tanh(h[0][2]), gelu_tanh(h[0][3]));
-                ha[2] = pack_bf16(gelu_tanh(h[1][0]), gelu_tanh(h[1][1])); ha[3] = pack_bf16(gelu_tanh(h[1][2]), gelu_tanh(h[1][3]));
+                float h[NW][2][4];
+                gemm_pair<KT, NW>(h, af, s_fc1, L::S_C, j, s_f + L::o_b1, g, tq);
+                uint32_t ha[NW][4];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    ha[w][0] = pack_bf16(gelu_tanh(h[w][0][0]), gelu_tanh(h[w][0][1])); ha[w][1] = pack_bf16(gelu_tanh(h[w][0][2]), gelu_tanh(h[w][0][3]));
+                    ha[w][2] = pack_bf16(gelu_tanh(h[w][1][0]), gelu_tanh(h[w][1][1])); ha[w][3] = pack_bf16(gelu_tanh(h[w][1][2]), gelu_tanh(h[w][1][3]));
+                }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const uint2 bf = lds64(s_fc2 + (size_t)wrow(nt, g) * L::S_H + j * 16 + 4 * tq);
-                    mma_bf16_16816(mo[nt], ha, bf.x, bf.y);
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) mma_bf16_16816(mo[w][nt], ha[w], bf.x, bf.y);
                 }
             }
 #pragma unroll
-            for (int kt = 0; kt < KT; ++kt) {
-                xa[kt].x += mo[2 * kt][0]; xa[kt].y += mo[2 * kt][1]; xa[kt].z += mo[2 * kt + 1][0]; xa[kt].w += mo[2 * kt + 1][1];
-                xb[kt].x += mo[2 * kt][2]; xb[kt].y += mo[2 * kt][3]; xb[kt].z += mo[2 * kt + 1][2]; xb[kt].w += mo[2 * kt + 1][3];
-            }
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    xa[w][kt].x += mo[w][2 * kt][0]; xa[w][kt].y += mo[w][2 * kt][1]; xa[w][kt].z += mo[w][2 * kt + 1][0]; xa[w][kt].w += mo[w][2 * kt + 1][1];
+                    xb[w][kt].x += mo[w][2 * kt][2]; xb[w][kt].y += mo[w][2 * kt][3]; xb[w][kt].z += mo[w][2 * kt + 1][2]; xb[w][kt].w += mo[w][2 * kt + 1][3];
+                }
         }
 #pragma unroll
-        for (int kt = 0; kt < KT; ++kt) { pa[4 * kt] = xa[kt]; pb[4 * kt] = xb[kt]; }
+        for (int w = 0; w < NW; ++w)
+            if (live[w]) {
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) { pa[w][4 * kt] = xa[w][kt]; pb[w][4 * kt] = xb[w][kt]; }
+            }
         if (p.dynamic) nxt = __shfl_sync(0xffffffffu, nxt, 0);
     }
     __syncthreads(); // every warp of this CTA has drawn its last index
     if (p.dynamic && threadIdx.x == 0 && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; } // last CTA re-arms the pair
 }
 
-template <int C, bool ATTN, bool MLP>
+template <int C, bool ATTN, bool MLP, int WARPS, int NW, int MINB>
 static int launch(const Params &p, cudaStream_t st)
 {
     using L = Layout<C, ATTN, MLP>;
     static_assert(L::bytes <= 227 * 1024, "weights do not fit shared memory");
-    auto kernel = swin_block_kernel<C, ATTN, MLP>;
+    auto kernel = swin_block_kernel<C, ATTN, MLP, WARPS, NW, MINB>;
     static PerDeviceSmem configured;
     if (L::bytes > 48 * 1024 && configured.needs(L::bytes)) {
         ICM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
         configured.done(L::bytes);
     }
     const long long n_win = (long long)p.B * (p.H / WIN) * (p.W / WIN);
-    const int warps = 8;
     static int per_sm = 0; // resident CTAs per SM (a property of the kernel: asked once)
-    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, L::bytes) != cudaSuccess || per_sm < 1)) per_sm = 1;
-    const long long want = (n_win + warps - 1) / warps;
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, L::bytes) != cudaSuccess || per_sm < 1)) per_sm = 1;
+    const long long want = (n_win + WARPS * NW - 1) / (WARPS * NW);
     const long long cap = (long long)persistent_grid_limit() * per_sm;
     Params q = p;
     q.sched = tile_counter(st);
     if (!q.sched) return ICM_ERR_CUDA;
     static const bool dyn = getenv("ICM_SWIN_STATIC") == nullptr;
     q.dynamic = dyn ? 1 : 0;
-    kernel<<<(unsigned)(want < cap ? want : cap), warps * 32, L::bytes, st>>>(q);
+    kernel<<<(unsigned)(want < cap ? want : cap), WARPS * 32, L::bytes, st>>>(q);
     ICM_LAUNCH_CHECK();
     return ICM_OK;
+}
+
+// Shape of the launch per instantiation (the fastest of the table above).  ICM_SWIN_SHAPE=<warps><windows><CTAs per SM> selects one of the
+// other compiled shapes for A/B measurements (1012: C = 48 with 10 warps; 811: C = 96 with 8 warps, the round-2 shape).
+template <int C, bool ATTN, bool MLP>
+static int launch_shaped(const Params &p, cudaStream_t st)
+{
+    static const int shape = getenv("ICM_SWIN_SHAPE") ? atoi(getenv("ICM_SWIN_SHAPE")) : 0;
+    if constexpr (C == 48) {
+        if (shape == 1012) return launch<C, ATTN, MLP, 10, 1, 2>(p, st);
+        return launch<C, ATTN, MLP, 8, 1, 2>(p, st);
+    } else {
+        if (shape == 811) return launch<C, ATTN, MLP, 8, 1, 1>(p, st);
+        return launch<C, ATTN, MLP, 12, 1, 1>(p, st);
+    }
 }
 
 }  // namespace sf
@@ -411,11 +469,11 @@ extern "C" int icm_swin_block(float *d_x, int B, int H, int W, int C, int heads,
     p.ln2_g = d_ln2_g; p.ln2_b = d_ln2_b; p.b_fc1 = d_b_fc1; p.b_fc2 = d_b_fc2;
     cudaStream_t st = as_stream(stream);
     if (C == 48) {
-        if (attn && mlp) return sf::launch<48, true, true>(p, st);
-        return attn ? sf::launch<48, true, false>(p, st) : sf::launch<48, false, true>(p, st);
+        if (attn && mlp) return sf::launch_shaped<48, true, true>(p, st);
+        return attn ? sf::launch_shaped<48, true, false>(p, st) : sf::launch_shaped<48, false, true>(p, st);
     }
     // C = 96: the four weight matrices together (221 KB + padding) exceed one CTA's shared memory: two passes
-    if (attn) { if (int rc = sf::launch<96, true, false>(p, st)) return rc; }
-    if (mlp) { if (int rc = sf::launch<96, false, true>(p, st)) return rc; }
+    if (attn) { if (int rc = sf::launch_shaped<96, true, false>(p, st)) return rc; }
+    if (mlp) { if (int rc = sf::launch_shaped<96, false, true>(p, st)) return rc; }
     return ICM_OK;
 }
