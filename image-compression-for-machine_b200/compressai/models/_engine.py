@@ -6,12 +6,16 @@ device memory and the stream; no torch operator does arithmetic on this path.
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from compressai import _native
 from compressai._native import (ACT_GELU, ACT_NONE, ACT_RSQRT, ACT_SIGMOID, ACT_SQRT, OUT_BF16, OUT_F32, RES_ADD, RES_ADD_BEFORE_ACT,
                                 RES_MUL, ConvArgs, ConvGroups, NativeError, check, lib, stream_ptr)
 
+
+_PITCH64 = os.environ.get("ICM_PITCH64", "1") != "0"  # A/B switch for Engine._pitch64
 
 class PackedConv:
     """bf16 [Cout_pad, KH*KW*Cin_pad] weight + fp32 bias on the device (icm_pack_conv_weight)."""
@@ -134,9 +138,20 @@ class Engine:
         return hit[0]
 
     # ---------------------------------------------------------------------------------- kernels
-    def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None, res_mode=0):
+    @staticmethod
+    def _pitch64(c):
+        """Row pitch (in channels) of an activation that only a following convolution reads: the next multiple of 64 channels
+        = 128 bytes.  The TMA engine of an SM moves 64-channel boxes at 111 B/clk when every pixel's 128-byte piece is one
+        aligned L2 line, 85 at a pitch of 448 bytes (C = 224) and 73 at 352 (C = 176) (tools/umma_issue_bench.cu), and the
+        N <= 176 layers of the context-model stacks are bound by exactly that rate."""
+        return (c + 63) // 64 * 64 if _PITCH64 else c
+
+    def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None, res_mode=0,
+             pitch64=False):
         """x: bf16 [.., pitch] channels-last holding B*H*W pixels.  Returns the output tensor
-        ([B*Ho*Wo(*r*r), Cout(/r^2)] unless `out` is given, then writes channels [out_offset, +Cout) of it)."""
+        ([B*Ho*Wo(*r*r), Cout(/r^2)] unless `out` is given, then writes channels [out_offset, +Cout) of it; with pitch64 the
+        rows of a new output are padded to a multiple of 64 channels -- the pad is never written and never read: the next
+        convolution reads Cin channels and TMA zero-fills the rest of its last 64-channel box)."""
         assert x.dtype == torch.bfloat16 and x.is_cuda
         in_pitch = x.shape[-1]
         cin = pk.Cin if cin is None else cin
@@ -147,7 +162,8 @@ class Engine:
         r = pk.ps if pk.ps else 1
         cout_eff = pk.Cout // (r * r)
         if out is None:
-            out = torch.empty((B * Ho * r * Wo * r, cout_eff), dtype=torch.float32 if out_dtype == OUT_F32 else torch.bfloat16, device=x.device)
+            out = torch.empty((B * Ho * r * Wo * r, self._pitch64(cout_eff) if pitch64 else cout_eff),
+                              dtype=torch.float32 if out_dtype == OUT_F32 else torch.bfloat16, device=x.device)
         a = ConvArgs()
         a.inp, a.weight = x.data_ptr(), pk.w.data_ptr()
         a.bias = pk.bias.data_ptr() if pk.bias is not None else None
@@ -164,7 +180,7 @@ class Engine:
         return out
 
     def conv_group(self, x, B, H, W, pg, in_images, in_offsets, tail_channels=None, out=None, out_offset=0, out_group_stride=None,
-                   act=ACT_NONE, out_dtype=OUT_BF16, cin=None):
+                   act=ACT_NONE, out_dtype=OUT_BF16, cin=None, pitch64=False):
         """G same-shaped convolutions in one launch (icm_conv2d_grouped).  x: bf16 channels-last tensor of `in_images` images;
         group g reads images [in_offsets[g], +B).  Output: stacked [G, B*Ho*Wo(*r*r), Cout(/r^2)] unless `out` is given, then group g
         writes at element offset out_offset + g * out_group_stride of it (row pitch = out.shape[-1])."""
@@ -178,7 +194,8 @@ class Engine:
         cout_eff = pg.Cout // (r * r)
         G = pg.G
         if out is None:
-            out = torch.empty((G, B * Ho * r * Wo * r, cout_eff), dtype=torch.float32 if out_dtype == OUT_F32 else torch.bfloat16, device=x.device)
+            out = torch.empty((G, B * Ho * r * Wo * r, self._pitch64(cout_eff) if pitch64 else cout_eff),
+                              dtype=torch.float32 if out_dtype == OUT_F32 else torch.bfloat16, device=x.device)
             out_group_stride = out.shape[1] * out.shape[2]
         a = ConvArgs()
         a.inp, a.weight = x.data_ptr(), pg.w.data_ptr()
@@ -221,7 +238,7 @@ class Engine:
                 x = self.conv_group(x, B, H, W, pg, ii, io, tc, out=final_out, out_offset=final_out_offset,
                                     out_group_stride=final_out_group_stride, act=final_act, out_dtype=final_dtype, **kw)
             else:
-                x = self.conv_group(x, B, H, W, pg, ii, io, tc, act=ACT_GELU, **kw)
+                x = self.conv_group(x, B, H, W, pg, ii, io, tc, act=ACT_GELU, pitch64=True, **kw)
             H = (H + 2 * pg.pad - pg.KH) // pg.stride + 1
             W = (W + 2 * pg.pad - pg.KW) // pg.stride + 1
             if ps:
@@ -325,7 +342,7 @@ class Engine:
             if last:
                 x = self.conv(x, B, H, W, pk, out=final_out, act=final_act, out_dtype=final_dtype, cin=cin if k == 0 else None)
             else:
-                x = self.conv(x, B, H, W, pk, act=ACT_GELU, cin=cin if k == 0 else None)
+                x = self.conv(x, B, H, W, pk, act=ACT_GELU, cin=cin if k == 0 else None, pitch64=True)
             H = (H + 2 * pk.pad - pk.KH) // pk.stride + 1
             W = (W + 2 * pk.pad - pk.KW) // pk.stride + 1
             if ps:

@@ -112,36 +112,44 @@ __global__ void __launch_bounds__(32) tma_bw(const __grid_constant__ CUtensorMap
 
 static int tma_bandwidth()
 {
-    const int rows_total = 1 << 18; // 2^18 rows x 128 B = 32 MB: L2-resident after the first pass
+    const int rows_total = 1 << 16; // pixels; at the widest pitch 2^16 x 512 B = 32 MB: L2-resident after the first pass
     void *buf;
-    if (cudaMalloc(&buf, (size_t)rows_total * 128) != cudaSuccess) return 1;
-    cudaMemset(buf, 0, (size_t)rows_total * 128);
+    if (cudaMalloc(&buf, (size_t)rows_total * 512) != cudaSuccess) return 1;
+    cudaMemset(buf, 0, (size_t)rows_total * 512);
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { printf("cuTensorMapEncodeTiled not available\n"); return 1; }
-    CUtensorMap map;
-    cuuint64_t dims[2] = {64, (cuuint64_t)rows_total}, strides[1] = {128};
-    cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
-    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("tensor map failed\n"); return 1; }
     long long *d_cyc;
     cudaMalloc(&d_cyc, 1024 * sizeof(long long));
     const size_t smem = 8 * 16384 + 1024;
     cudaFuncSetAttribute(tma_bw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    printf("\nL2 -> shared memory, TMA 2-D boxes of 16 KB (128 rows x 128 B, SWIZZLE_128B), 8 in flight per CTA, 32 MB buffer (second pass: L2 hits)\n");
-    printf("%5s | %12s %12s | %12s\n", "CTAs", "B/clk/SM avg", "B/clk/SM min", "B/clk chip");
+    printf("\nL2 -> shared memory, TMA 2-D boxes of 16 KB (64 channels x 128 pixels, SWIZZLE_128B), 8 in flight per CTA, L2-resident buffer (second pass);\n"
+           "pitch = bytes between pixels (channels-last activation with C = pitch / 2 channels), c0 = first channel of the box\n");
+    printf("%5s %5s %5s | %12s %12s | %12s\n", "pitch", "c0", "CTAs", "B/clk/SM avg", "B/clk/SM min", "B/clk chip");
     const int n_loads = 2048;
-    for (int grid : {1, 8, 37, 74, 148}) {
-        std::vector<long long> h(grid);
-        for (int pass = 0; pass < 2; ++pass) {
-            tma_bw<<<grid, 32, smem>>>(map, n_loads, rows_total, d_cyc);
-            cudaError_t e = cudaDeviceSynchronize();
-            if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+    for (int pitch : {128, 256, 352, 384, 448, 512})
+        for (int c0 : {0, 64}) {
+            if (c0 * 2 + 128 > pitch) continue;
+            CUtensorMap map;
+            cuuint64_t dims[2] = {(cuuint64_t)(pitch / 2), (cuuint64_t)rows_total}, strides[1] = {(cuuint64_t)pitch};
+            cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+            if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (char *)buf + c0 * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+                printf("tensor map failed (pitch %d)\n", pitch);
+                continue;
+            }
+            for (int grid : {1, 148}) {
+                std::vector<long long> h(grid);
+                for (int pass = 0; pass < 2; ++pass) {
+                    tma_bw<<<grid, 32, smem>>>(map, n_loads, rows_total, d_cyc);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+                }
+                cudaMemcpy(h.data(), d_cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+                double sum = 0, mn = 1e30;
+                for (long long c : h) { const double bw = (double)n_loads * 16384 / (double)c; sum += bw; mn = bw < mn ? bw : mn; }
+                printf("%5d %5d %5d | %12.1f %12.1f | %12.0f\n", pitch, c0, grid, sum / grid, mn, sum);
+            }
         }
-        cudaMemcpy(h.data(), d_cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
-        double sum = 0, mn = 1e30;
-        for (long long c : h) { const double bw = (double)n_loads * 16384 / (double)c; sum += bw; mn = bw < mn ? bw : mn; }
-        printf("%5d | %12.1f %12.1f | %12.0f\n", grid, sum / grid, mn, sum);
-    }
     return 0;
 }
 
