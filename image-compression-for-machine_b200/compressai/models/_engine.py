@@ -5,7 +5,6 @@ parameter holders; `swin_block()` etc. string the kernels of csrc/transforms.cu 
 device memory and the stream; no torch operator does arithmetic on this path.
 """
 import ctypes as C
-
 import os
 
 import torch
@@ -14,8 +13,8 @@ from compressai import _native
 from compressai._native import (ACT_GELU, ACT_NONE, ACT_RSQRT, ACT_SIGMOID, ACT_SQRT, OUT_BF16, OUT_F32, RES_ADD, RES_ADD_BEFORE_ACT,
                                 RES_MUL, ConvArgs, ConvGroups, NativeError, check, lib, stream_ptr)
 
-
 _PITCH64 = os.environ.get("ICM_PITCH64", "1") != "0"  # A/B switch for Engine._pitch64
+
 
 class PackedConv:
     """bf16 [Cout_pad, KH*KW*Cin_pad] weight + fp32 bias on the device (icm_pack_conv_weight)."""
@@ -142,8 +141,9 @@ class Engine:
     def _pitch64(c):
         """Row pitch (in channels) of an activation that only a following convolution reads: the next multiple of 64 channels
         = 128 bytes.  The TMA engine of an SM moves 64-channel boxes at 111 B/clk when every pixel's 128-byte piece is one
-        aligned L2 line, 85 at a pitch of 448 bytes (C = 224) and 73 at 352 (C = 176) (tools/umma_issue_bench.cu), and the
-        N <= 176 layers of the context-model stacks are bound by exactly that rate."""
+        aligned L2 line, 85 at a pitch of 448 bytes (C = 224) and 73 at 352 (C = 176) (tools/umma_issue_bench.cu), and in the
+        N <= 176 layers of the context-model stacks that ingest takes as long as the MMAs: 176 -> 128 layers
+        +6-9 %, 224 -> 176 +2.5 % (profiles/r02_conv_pitch_ab.txt)."""
         return (c + 63) // 64 * 64 if _PITCH64 else c
 
     def conv(self, x, B, H, W, pk, out=None, out_offset=0, act=ACT_NONE, out_dtype=OUT_BF16, residual=None, cin=None, res_mode=0,

@@ -185,10 +185,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int img = b + p.a_img[g], wrow = n0 + g * p.w_group_rows;
                 const int tail_c = p.has_tail ? p.tail_ch[g] : (p.k_chunks - 1) * BK;
                 // (tap, chunk) -> (dy, dx, channel, weight column) advance by counters: this one thread issues every load of the
-                // CTA, and the two runtime integer divisions a k-step used to start with (it / k_chunks, tap / KW: ~25 dependent
-                // instructions each, ~5 cycles apiece in a lone thread) made the k-step period ~400-500 cycles whatever N --
-                // longer than the four MMAs of a k-step take for N <= 176 (tools/umma_issue_bench.cu: 40 / 48 / 64 / 96 cycles
-                // per MMA at N = 32 / 64 / 128 / 192), so those layers were bound by this loop, not by the tensor pipe.
+                // CTA, and a k-step used to start with two runtime integer divisions (it / k_chunks, tap / KW: ~25 dependent
+                // instructions each at ~5 cycles apiece in a lone thread).  For N <= 176 the four MMAs of a k-step take only
+                // 160-350 cycles (tools/umma_issue_bench.cu: 40 / 48 / 64 / 96 cycles per MMA at N = 32 / 64 / 128 / 192) and
+                // the TMA ingest about as long, so this prologue was on the critical path: conv family 34.5 -> 33.7 ms per step.
                 const int wx0 = w0 * p.stride - p.pad, hy0 = h0 * p.stride - p.pad, last_chunk = p.k_chunks - 1;
                 int chunk = 0, dx = 0, dy = 0, wcol = 0, ch = 0;
                 for (int it = 0; it < k_iters; ++it) {
